@@ -1,0 +1,427 @@
+// C ABI of libtreasure_b200.so (include/treasure_b200.h): level compiler, batch
+// lifetime, and the stream-ordered entry points.  Host code only; kernels live in
+// tg_step.cu / tg_render.cu.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "tg_launch.h"
+
+using namespace tg;
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(TG_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ---------------------------------------------------------------------------
+// objects behind the opaque handles
+// ---------------------------------------------------------------------------
+struct tg_level {
+    LevelBlob blob;
+    tg_level_info info;
+    std::vector<uint8_t> background;   // frame_h * frame_w * 3
+    std::vector<uint32_t> sprites;     // TG_NUM_SPRITES * 48 * 48
+};
+
+struct tg_env {
+    int device = 0;
+    int n_levels = 0;
+    int ni = 2;                        // kernel specialisation: 2 or 4 item slots
+    BatchView B{};
+    RenderView R{};
+    bool has_render = false;
+    std::vector<void *> allocs;        // everything cudaMalloc'ed for this env
+    // device-side staging for tg_step_host (owned through `allocs`)
+    int32_t *s_actions = nullptr; float *s_obs = nullptr; float *s_reward = nullptr;
+    uint8_t *s_done = nullptr; uint8_t *s_ran = nullptr;
+    int64_t launches = 0;
+};
+
+extern "C" const char *tg_last_error(void) { return g_err; }
+extern "C" int tg_abi_version(void) { return TG_ABI_VERSION; }
+extern "C" int tg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---------------------------------------------------------------------------
+// level compiler (host)
+// ---------------------------------------------------------------------------
+extern "C" int tg_level_create(const uint8_t *tiles, int32_t cw, int32_t ch, const tg_object *objs, int32_t n_objs,
+                               const tg_trigger *trigs, int32_t n_trigs, tg_level **out) {
+    if (!tiles || !out || (n_objs > 0 && !objs) || (n_trigs > 0 && !trigs)) return fail(TG_ERR_ARG, "null argument");
+    if (cw < 1 || ch < 1 || cw > TG_MAX_GRID || ch > TG_MAX_GRID) return fail(TG_ERR_ARG, "grid %dx%d outside 1..%d", cw, ch, TG_MAX_GRID);
+    if (n_objs < 0 || n_objs > TG_MAX_OBJECTS) return fail(TG_ERR_ARG, "%d objects (max %d)", n_objs, TG_MAX_OBJECTS);
+    if (n_trigs < 0 || n_trigs > TG_MAX_TRIGGERS) return fail(TG_ERR_ARG, "%d triggers (max %d)", n_trigs, TG_MAX_TRIGGERS);
+    tg_level *lv = new (std::nothrow) tg_level();
+    if (!lv) return fail(TG_ERR_NOMEM, "out of host memory");
+    LevelBlob &b = lv->blob;
+    memset(&b, 0, sizeof b);
+    memset(b.tiles, T_WALL, sizeof b.tiles);                 // out of bounds reads as WALL (impl:220-223)
+    b.cw = (int16_t)cw; b.ch = (int16_t)ch;
+    b.start_px = b.start_py = -1;
+    for (int y = 0; y < ch; y++)
+        for (int x = 0; x < cw; x++) {
+            const uint8_t c = tiles[y * cw + x];
+            int t;
+            if (c == ' ') t = T_OPEN; else if (c == '/') t = T_WALL; else if (c == 'L') t = T_LADDER;
+            else { delete lv; return fail(TG_ERR_ARG, "tile (%d,%d) has unsupported character 0x%02x", x, y, c); }
+            b.tiles[(y + PAD) * TSTRIDE + x + PAD] = (uint8_t)t;
+            if (t != T_WALL && b.start_px < 0) { b.start_px = (int16_t)(x * S + S / 2); b.start_py = (int16_t)(y * S); lv->info.start_cx = x; lv->info.start_cy = y; }
+        }
+    if (b.start_px < 0) { lv->info.start_cx = lv->info.start_cy = -1; }
+    uint32_t flags = 1u << F_FACING;
+    int obs = 2;
+    int obj_of[5][TG_MAX_OBJECTS];
+    int cnt[5] = {0, 0, 0, 0, 0};
+    int n_items = 0;
+    for (int o = 0; o < n_objs; o++) {
+        const tg_object &ob = objs[o];
+        if (ob.kind < 0 || ob.kind > 4) { delete lv; return fail(TG_ERR_ARG, "object %d: unknown kind %d", o, ob.kind); }
+        if (ob.cx < 0 || ob.cx >= cw || ob.cy < 0 || ob.cy >= ch) { delete lv; return fail(TG_ERR_ARG, "object %d outside the grid", o); }
+        uint8_t &code = b.tiles[(ob.cy + PAD) * TSTRIDE + ob.cx + PAD];
+        b.obj_kind[o] = (uint8_t)ob.kind;
+        b.obj_obs[o] = 255;
+        obj_of[ob.kind][cnt[ob.kind]] = o;
+        int idx;
+        switch (ob.kind) {
+        case TG_DOOR:
+            idx = b.n_doors;
+            if (idx >= TG_MAX_DOORS) { delete lv; return fail(TG_ERR_ARG, "more than %d doors", TG_MAX_DOORS); }
+            if (code & TC_HAS_DOOR) { delete lv; return fail(TG_ERR_ARG, "two doors share cell (%d,%d)", ob.cx, ob.cy); }
+            code = (uint8_t)((code & TC_STATIC_OBJ) | TC_HAS_DOOR | (idx << 4));
+            b.door_cx[idx] = (int8_t)ob.cx; b.door_cy[idx] = (int8_t)ob.cy; b.door_obj[idx] = (uint8_t)o;
+            if (ob.flag) flags |= 1u << (F_DOORS + idx);
+            b.n_doors++;
+            break;
+        case TG_HANDLE:
+            idx = b.n_handles;
+            if (idx >= TG_MAX_HANDLES) { delete lv; return fail(TG_ERR_ARG, "more than %d handles", TG_MAX_HANDLES); }
+            code |= TC_STATIC_OBJ;
+            b.handle_cx[idx] = (int8_t)ob.cx; b.handle_cy[idx] = (int8_t)ob.cy; b.handle_obj[idx] = (uint8_t)o;
+            if (ob.flag) flags |= 1u << (F_HANDLES + idx);
+            b.obj_obs[o] = (uint8_t)obs; obs += 1;
+            b.n_handles++;
+            break;
+        case TG_BOLT:
+            idx = b.n_bolts;
+            if (idx >= TG_MAX_BOLTS) { delete lv; return fail(TG_ERR_ARG, "more than %d bolts", TG_MAX_BOLTS); }
+            code |= TC_STATIC_OBJ;
+            b.bolt_cx[idx] = (int8_t)ob.cx; b.bolt_cy[idx] = (int8_t)ob.cy; b.bolt_obj[idx] = (uint8_t)o;
+            if (ob.flag) flags |= 1u << (F_BOLTS + idx);
+            b.obj_obs[o] = (uint8_t)obs; obs += 1;
+            b.n_bolts++;
+            break;
+        default:   // key, gold
+            idx = n_items;
+            if (idx >= TG_MAX_ITEMS) { delete lv; return fail(TG_ERR_ARG, "more than %d keys+gold", TG_MAX_ITEMS); }
+            b.item_cx[idx] = (int8_t)ob.cx; b.item_cy[idx] = (int8_t)ob.cy; b.item_obj[idx] = (uint8_t)o;
+            if (ob.kind == TG_KEY) b.key_mask |= (uint8_t)(1u << idx); else b.gold_mask |= 1u << idx;
+            b.obj_obs[o] = (uint8_t)obs; obs += 2;
+            n_items++;
+            break;
+        }
+        b.obj_idx[o] = (uint8_t)idx;
+        cnt[ob.kind]++;
+    }
+    b.n_items = (uint8_t)n_items; b.n_objs = (uint8_t)n_objs; b.obs_dim = (uint8_t)obs;
+    b.init_flags = flags;
+    // bag slots are the cells (cw-1-k, ch-1) (impl:353); they must be unreachable, i.e. plain WALL,
+    // so that an item in the bag can never be picked up a second time
+    for (int k = 0; k < n_items; k++) {
+        const int bx = cw - 1 - k, by = ch - 1;
+        if (bx < 0 || b.tiles[(by + PAD) * TSTRIDE + bx + PAD] != T_WALL) {
+            delete lv;
+            return fail(TG_ERR_ARG, "bag cell (%d,%d) must be a wall cell without objects", bx, by);
+        }
+    }
+    for (int t = 0; t < n_trigs; t++) {
+        const tg_trigger &tr = trigs[t];
+        const bool ok1 = tr.src_kind == TG_DOOR || tr.src_kind == TG_HANDLE || tr.src_kind == TG_BOLT;
+        const bool ok2 = tr.dst_kind == TG_DOOR || tr.dst_kind == TG_HANDLE || tr.dst_kind == TG_BOLT;
+        if (!ok1 || !ok2 || tr.src_index < 0 || tr.src_index >= cnt[tr.src_kind] || tr.dst_index < 0 || tr.dst_index >= cnt[tr.dst_kind]) {
+            delete lv;
+            return fail(TG_ERR_ARG, "trigger %d references a missing object", t);
+        }
+        b.trig_src[t] = (uint8_t)(obj_of[tr.src_kind][tr.src_index] | (tr.src_value ? 128 : 0));
+        b.trig_dst[t] = (uint8_t)(obj_of[tr.dst_kind][tr.dst_index] | (tr.dst_value ? 128 : 0));
+    }
+    b.n_trigs = (uint8_t)n_trigs;
+    b.inv_w = 1.0f / (float)(cw * S); b.inv_h = 1.0f / (float)(ch * S);
+    tg_level_info &I = lv->info;
+    I.cw = cw; I.ch = ch; I.n_doors = b.n_doors; I.n_handles = b.n_handles; I.n_bolts = b.n_bolts; I.n_items = n_items;
+    I.n_objects = n_objs; I.n_triggers = n_trigs; I.obs_dim = obs; I.frame_w = cw * S; I.frame_h = ch * S; I.has_sprites = 0;
+    *out = lv;
+    return TG_OK;
+}
+
+extern "C" int tg_level_get_info(const tg_level *lv, tg_level_info *out) {
+    if (!lv || !out) return fail(TG_ERR_ARG, "null argument");
+    *out = lv->info;
+    return TG_OK;
+}
+
+extern "C" int tg_level_set_sprites(tg_level *lv, const uint8_t *sprites_rgba, const uint8_t *background_rgb) {
+    if (!lv || !sprites_rgba || !background_rgb) return fail(TG_ERR_ARG, "null argument");
+    const size_t nb = (size_t)lv->info.frame_w * lv->info.frame_h * 3;
+    lv->background.assign(background_rgb, background_rgb + nb);
+    lv->sprites.resize((size_t)TG_NUM_SPRITES * S * S);
+    memcpy(lv->sprites.data(), sprites_rgba, lv->sprites.size() * 4);   // bytes R,G,B,A == little-endian R|G<<8|B<<16|A<<24
+    lv->info.has_sprites = 1;
+    return TG_OK;
+}
+
+extern "C" void tg_level_destroy(tg_level *lv) { delete lv; }
+
+// ---------------------------------------------------------------------------
+// batch lifetime
+// ---------------------------------------------------------------------------
+template <typename T>
+static cudaError_t dev_alloc(tg_env *e, T **p, size_t count) {
+    void *q = nullptr;
+    cudaError_t r = cudaMalloc(&q, count * sizeof(T) ? count * sizeof(T) : 16);
+    if (r == cudaSuccess) { e->allocs.push_back(q); *p = static_cast<T *>(q); }
+    return r;
+}
+
+static void free_env(tg_env *e) {
+    if (!e) return;
+    for (void *p : e->allocs) cudaFree(p);
+    delete e;
+}
+
+extern "C" int tg_create(const tg_level *const *levels, int32_t n_levels, const uint8_t *level_ids, int64_t num_envs,
+                         int64_t first_env_id, int32_t device, uint64_t seed, int32_t max_episode_steps,
+                         int32_t auto_reset, tg_env **out) {
+    if (!levels || !out) return fail(TG_ERR_ARG, "null argument");
+    if (n_levels < 1 || n_levels > TG_MAX_LEVELS) return fail(TG_ERR_ARG, "n_levels %d outside 1..%d", n_levels, TG_MAX_LEVELS);
+    if (num_envs < 1) return fail(TG_ERR_ARG, "num_envs must be positive");
+    if (max_episode_steps < 0) return fail(TG_ERR_ARG, "max_episode_steps must be >= 0");
+    for (int l = 0; l < n_levels; l++) if (!levels[l]) return fail(TG_ERR_ARG, "level %d is null", l);
+    if (level_ids)
+        for (int64_t i = 0; i < num_envs; i++)
+            if (level_ids[i] >= n_levels) return fail(TG_ERR_ARG, "level_ids[%lld] = %d out of range", (long long)i, level_ids[i]);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(TG_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(TG_ERR_ARG, "device %d outside 0..%d", device, ndev - 1);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(TG_ERR_CUDA, "cannot select device %d", device);
+
+    tg_env *e = new (std::nothrow) tg_env();
+    if (!e) return fail(TG_ERR_NOMEM, "out of host memory");
+    e->device = device; e->n_levels = n_levels;
+    BatchView &B = e->B;
+    B.n = num_envs; B.first_env_id = first_env_id; B.n_levels = n_levels;
+    B.max_steps = max_episode_steps; B.auto_reset = auto_reset ? 1 : 0;
+    B.seed_lo = (uint32_t)seed; B.seed_hi = (uint32_t)(seed >> 32);
+    int max_items = 0, obs_dim = 0;
+    bool all_sprites = true, same_size = true;
+    for (int l = 0; l < n_levels; l++) {
+        if (levels[l]->info.n_items > max_items) max_items = levels[l]->info.n_items;
+        if (levels[l]->info.obs_dim > obs_dim) obs_dim = levels[l]->info.obs_dim;
+        all_sprites = all_sprites && levels[l]->info.has_sprites;
+        same_size = same_size && levels[l]->info.cw == levels[0]->info.cw && levels[l]->info.ch == levels[0]->info.ch;
+    }
+    e->ni = (max_items <= 2) ? 2 : 4;
+    B.obs_dim = obs_dim;
+
+#define CUE(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) { free_env(e); return fail(TG_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } \
+    } while (0)
+
+    LevelBlob *d_levels = nullptr;
+    CUE(dev_alloc(e, &d_levels, (size_t)n_levels));
+    for (int l = 0; l < n_levels; l++) CUE(cudaMemcpy(d_levels + l, &levels[l]->blob, sizeof(LevelBlob), cudaMemcpyHostToDevice));
+    B.levels = d_levels;
+    CUE(dev_alloc(e, &B.core, (size_t)num_envs));
+    CUE(dev_alloc(e, &B.acct, (size_t)num_envs));
+    CUE(cudaMemset(B.core, 0, sizeof(uint4) * (size_t)num_envs));
+    CUE(cudaMemset(B.acct, 0, sizeof(uint4) * (size_t)num_envs));
+    if (e->ni > 2) { CUE(dev_alloc(e, &B.items23, (size_t)num_envs)); CUE(cudaMemset(B.items23, 0, sizeof(uint2) * (size_t)num_envs)); }
+    CUE(dev_alloc(e, &B.angles, (size_t)num_envs * TG_MAX_HANDLES));
+    CUE(cudaMemset(B.angles, 0, sizeof(double) * (size_t)num_envs * TG_MAX_HANDLES));
+    if (level_ids && n_levels > 1) {
+        uint8_t *d_ids = nullptr;
+        CUE(dev_alloc(e, &d_ids, (size_t)num_envs));
+        CUE(cudaMemcpy(d_ids, level_ids, (size_t)num_envs, cudaMemcpyHostToDevice));
+        B.level_id = d_ids;
+    }
+    CUE(dev_alloc(e, &B.stats, (size_t)8));
+    CUE(cudaMemset(B.stats, 0, 64));
+    if (all_sprites && same_size) {
+        RenderView &R = e->R;
+        R.frame_w = levels[0]->info.frame_w; R.frame_h = levels[0]->info.frame_h;
+        R.cw = levels[0]->info.cw; R.ch = levels[0]->info.ch;
+        for (int l = 0; l < n_levels; l++) {
+            uint8_t *bg = nullptr; uint32_t *sp = nullptr;
+            CUE(dev_alloc(e, &bg, levels[l]->background.size()));
+            CUE(cudaMemcpy(bg, levels[l]->background.data(), levels[l]->background.size(), cudaMemcpyHostToDevice));
+            CUE(dev_alloc(e, &sp, levels[l]->sprites.size()));
+            CUE(cudaMemcpy(sp, levels[l]->sprites.data(), levels[l]->sprites.size() * 4, cudaMemcpyHostToDevice));
+            R.assets[l].background = bg; R.assets[l].sprites = sp;
+        }
+        e->has_render = true;
+    }
+    // constructor draws + initial state (impl:31-53)
+    CUE(launch_reset(B, e->ni, nullptr, nullptr, 0));
+    e->launches++;
+    CUE(cudaDeviceSynchronize());
+#undef CUE
+    *out = e;
+    return TG_OK;
+}
+
+extern "C" void tg_destroy(tg_env *env) {
+    if (!env) return;
+    DeviceGuard guard(env->device);
+    cudaDeviceSynchronize();
+    free_env(env);
+}
+
+extern "C" int64_t tg_num_envs(const tg_env *env) { return env ? env->B.n : 0; }
+extern "C" int32_t tg_obs_dim(const tg_env *env) { return env ? env->B.obs_dim : 0; }
+extern "C" int64_t tg_launch_count(const tg_env *env) { return env ? env->launches : 0; }
+
+// ---------------------------------------------------------------------------
+// stream-ordered entry points
+// ---------------------------------------------------------------------------
+extern "C" int tg_reset(tg_env *env, const uint8_t *mask, float *obs, void *stream) {
+    if (!env) return fail(TG_ERR_ARG, "null env");
+    DeviceGuard guard(env->device);
+    CU(launch_reset(env->B, env->ni, mask, obs, (cudaStream_t)stream));
+    env->launches++;
+    return TG_OK;
+}
+
+extern "C" int tg_step(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done, uint8_t *ran,
+                       uint16_t *avail, void *stream) {
+    if (!env || !actions) return fail(TG_ERR_ARG, "null argument");
+    DeviceGuard guard(env->device);
+    CU(launch_step(env->B, env->ni, actions, obs, reward, done, ran, avail, (cudaStream_t)stream));
+    env->launches++;
+    return TG_OK;
+}
+
+static int ensure_staging(tg_env *env) {
+    if (env->s_ran) return TG_OK;
+    const size_t n = (size_t)env->B.n;
+    CU(dev_alloc(env, &env->s_actions, n));
+    CU(dev_alloc(env, &env->s_obs, n * env->B.obs_dim));
+    CU(dev_alloc(env, &env->s_reward, n));
+    CU(dev_alloc(env, &env->s_done, n));
+    CU(dev_alloc(env, &env->s_ran, n));
+    return TG_OK;
+}
+
+extern "C" int tg_step_host(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done,
+                            uint8_t *ran, void *stream) {
+    if (!env || !actions) return fail(TG_ERR_ARG, "null argument");
+    DeviceGuard guard(env->device);
+    int rc = ensure_staging(env);
+    if (rc != TG_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)env->B.n;
+    CU(cudaMemcpyAsync(env->s_actions, actions, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    CU(launch_step(env->B, env->ni, env->s_actions, obs ? env->s_obs : nullptr, reward ? env->s_reward : nullptr,
+                   done ? env->s_done : nullptr, ran ? env->s_ran : nullptr, nullptr, s));
+    env->launches++;
+    if (obs) CU(cudaMemcpyAsync(obs, env->s_obs, n * env->B.obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (reward) CU(cudaMemcpyAsync(reward, env->s_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (done) CU(cudaMemcpyAsync(done, env->s_done, n, cudaMemcpyDeviceToHost, s));
+    if (ran) CU(cudaMemcpyAsync(ran, env->s_ran, n, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return TG_OK;
+}
+
+extern "C" int tg_available_mask(tg_env *env, uint8_t *mask, void *stream) {
+    if (!env || !mask) return fail(TG_ERR_ARG, "null argument");
+    DeviceGuard guard(env->device);
+    CU(launch_mask(env->B, env->ni, mask, (cudaStream_t)stream));
+    env->launches++;
+    return TG_OK;
+}
+
+extern "C" int tg_render(tg_env *env, int64_t first, int64_t count, uint8_t *frames, void *stream) {
+    if (!env || !frames) return fail(TG_ERR_ARG, "null argument");
+    if (!env->has_render) return fail(TG_ERR_STATE, "render needs tg_level_set_sprites on every level (and equal grid sizes)");
+    if (first < 0 || count < 0 || first + count > env->B.n) return fail(TG_ERR_ARG, "frame range outside the batch");
+    if (count == 0) return TG_OK;
+    DeviceGuard guard(env->device);
+    CU(launch_render(env->B, env->R, first, count, frames, (cudaStream_t)stream));
+    env->launches += (count + 32767) / 32768;
+    return TG_OK;
+}
+
+extern "C" int tg_get_state(tg_env *env, const tg_state_view *out, void *stream) {
+    if (!env || !out) return fail(TG_ERR_ARG, "null argument");
+    DeviceGuard guard(env->device);
+    CU(launch_get_state(env->B, *out, (cudaStream_t)stream));
+    env->launches++;
+    return TG_OK;
+}
+
+extern "C" int tg_set_state(tg_env *env, const tg_state_view *in, void *stream) {
+    if (!env || !in) return fail(TG_ERR_ARG, "null argument");
+    DeviceGuard guard(env->device);
+    CU(launch_set_state(env->B, *in, (cudaStream_t)stream));
+    env->launches++;
+    return TG_OK;
+}
+
+extern "C" int tg_set_draw_tape(tg_env *env, const double *tape, const int64_t *offsets, void *stream) {
+    if (!env) return fail(TG_ERR_ARG, "null env");
+    if ((tape == nullptr) != (offsets == nullptr)) return fail(TG_ERR_ARG, "tape and offsets must both be set or both be null");
+    DeviceGuard guard(env->device);
+    env->B.tape = tape; env->B.tape_off = offsets;
+    // draw indices restart at 0: acct.x is the first word of each 16-byte record
+    CU(cudaMemset2DAsync(env->B.acct, sizeof(uint4), 0, sizeof(uint32_t), (size_t)env->B.n, (cudaStream_t)stream));
+    return TG_OK;
+}
+
+extern "C" int tg_stats(tg_env *env, int64_t *out8, void *stream) {
+    if (!env || !out8) return fail(TG_ERR_ARG, "null argument");
+    DeviceGuard guard(env->device);
+    CU(cudaMemcpyAsync(out8, env->B.stats, 64, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return TG_OK;
+}
+
+extern "C" int tg_stats_clear(tg_env *env, void *stream) {
+    if (!env) return fail(TG_ERR_ARG, "null env");
+    DeviceGuard guard(env->device);
+    CU(cudaMemsetAsync(env->B.stats, 0, 64, (cudaStream_t)stream));
+    return TG_OK;
+}

@@ -1,0 +1,540 @@
+// Device-side dynamics of the Treasure Game: one thread owns one environment.
+//
+// The formulation is cell-granular bit-tests on a padded byte table in shared
+// memory (the reference's 672x624 character map is provably cell-granular:
+// _treasure_game_impl.py:204-216 appends the same row list 48 times and doors patch
+// whole cells, _objects.py:246-253), state packed in registers, counter-based RNG.
+// Citations: impl = _treasure_game_impl/_treasure_game_impl.py, opts = _move_options.py,
+// opt = _option.py, objs = _objects.py, tg = treasure_game.py (all under
+// /root/reference/gym_treasure_game/envs/).
+#pragma once
+#include <cuda_runtime.h>
+#include "tg_types.h"
+
+namespace tg {
+
+// ---------------------------------------------------------------------------
+// per-thread working state
+// ---------------------------------------------------------------------------
+template <int NI>
+struct Env {
+    int px, py;
+    uint32_t flags;
+    int ix[NI], iy[NI];          // item (key / gold) pixel positions
+    uint32_t draws;              // uniforms consumed by this env since creation
+    uint32_t total_actions;      // impl:53,295 (per episode)
+    // RNG
+    uint32_t blk, w0, w1, w2, w3;   // cached Philox block
+    uint32_t key0, key1, id_lo, id_hi;
+    const double *tape;             // parity mode: this env's slice of the draw tape
+    // where this env's handle angles live (touched only by interact / reset / obs)
+    double *angles;              // angles[h * n] is handle h
+    int64_t n;
+};
+
+__device__ __forceinline__ bool facing(uint32_t f) { return (f >> F_FACING) & 1u; }
+__device__ __forceinline__ int ticker(uint32_t f) { return (f >> F_TICKER) & 31u; }
+__device__ __forceinline__ uint32_t set_ticker(uint32_t f, int t) {
+    return (f & ~(31u << F_TICKER)) | ((uint32_t)t << F_TICKER);
+}
+__device__ __forceinline__ int bag_len(uint32_t f) { return __popc((f >> F_INBAG) & ((1u << TG_MAX_ITEMS) - 1)); }
+
+// ---------------------------------------------------------------------------
+// RNG: Philox4x32-10, two 53-bit uniforms per block (same construction as
+// CPython's random(): (a>>5, b>>6) -> (a*2^26+b)/2^53).
+// ctr = (draw_index >> 1, 0, env_id_lo, env_id_hi), key = (seed_lo, seed_hi)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1,
+                                              uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
+template <bool TAPE, int NI>
+__device__ __forceinline__ double draw(Env<NI> &e) {
+    uint32_t d = e.draws++;
+    if (TAPE) return e.tape[d];
+    uint32_t b = d >> 1;
+    if (b != e.blk) {
+        philox4x32_10(b, 0u, e.id_lo, e.id_hi, e.key0, e.key1, e.w0, e.w1, e.w2, e.w3);
+        e.blk = b;
+    }
+    uint32_t a = (d & 1u) ? e.w2 : e.w0, c = (d & 1u) ? e.w3 : e.w1;
+    return ((double)(a >> 5) * 67108864.0 + (double)(c >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// CPython random.uniform(a, b) = a + (b - a) * random(): two separately rounded operations.
+__device__ __forceinline__ double uniform_span(double lo, double span, double u) {
+    return __dadd_rn(lo, __dmul_rn(span, u));
+}
+// objs:111-114 / objs:127-131: angle for an up (0.85..1) or down (0..0.15) handle
+__device__ __forceinline__ double handle_angle(bool up, double u) {
+    // (1.0 - 0.85) evaluates to 0.15000000000000002 in binary64, as in CPython
+    return up ? uniform_span(0.85, 1.0 - 0.85, u) : uniform_span(0.0, 0.15, u);
+}
+
+// ---------------------------------------------------------------------------
+// tiles
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int pad_cell(int v) {       // pixel -> padded cell index (floor(v/48)+PAD)
+    int t = max(v + PAD * S, 0);
+    return min((int)((unsigned)t / (unsigned)S), TSTRIDE - 1);
+}
+__device__ __forceinline__ int pad_idx(int c) { return min(max(c + PAD, 0), TSTRIDE - 1); }
+
+// effective type of the cell with padded indices (ixp, iyp)    impl:218-225 + objs:246-253
+__device__ __forceinline__ int type_p(const LevelBlob &L, uint32_t flags, int ixp, int iyp) {
+    int code = L.tiles[iyp * TSTRIDE + ixp];
+    int d = (flags >> (F_DOORS + (code >> 4))) & 1u;
+    return (code & TC_HAS_DOOR) ? d * T_DOOR : (code & 3);
+}
+// impl:227-230 object_type_at_cell
+__device__ __forceinline__ int type_c(const LevelBlob &L, uint32_t flags, int cx, int cy) {
+    return type_p(L, flags, pad_idx(cx), pad_idx(cy));
+}
+
+// impl:283-288  (x +- 10, y + {0, 50}) all OPEN
+__device__ __forceinline__ bool can_fall(const LevelBlob &L, uint32_t flags, int px, int py) {
+    int c0 = pad_cell(px - 10), c1 = pad_cell(px + 10), r0 = pad_cell(py), r1 = pad_cell(py + 50);
+    int t = type_p(L, flags, c0, r0) | type_p(L, flags, c1, r0) | type_p(L, flags, c0, r1) | type_p(L, flags, c1, r1);
+    return t == T_OPEN;
+}
+// impl:232-238  (x + {-4,0,4}, y + {-4..-1}) all OPEN; the probes span <= 2 columns and <= 2 rows
+__device__ __forceinline__ bool up_clear(const LevelBlob &L, uint32_t flags, int px, int py) {
+    int c0 = pad_cell(px - 4), c1 = pad_cell(px + 4), r0 = pad_cell(py - 4), r1 = pad_cell(py - 1);
+    int t = type_p(L, flags, c0, r0) | type_p(L, flags, c1, r0) | type_p(L, flags, c0, r1) | type_p(L, flags, c1, r1);
+    return t == T_OPEN;
+}
+// impl:240-250  y > 1 and a LADDER at (x +- 12, y + {-4, 0, 44})
+__device__ __forceinline__ bool can_go_up(const LevelBlob &L, uint32_t flags, int px, int py) {
+    if (py <= 1) return false;
+    int c0 = pad_cell(px - 12), c1 = pad_cell(px + 12);
+    int r0 = pad_cell(py - 4), r1 = pad_cell(py), r2 = pad_cell(py + 44);
+    bool l = false;
+    l |= type_p(L, flags, c0, r0) == T_LADDER; l |= type_p(L, flags, c1, r0) == T_LADDER;
+    l |= type_p(L, flags, c0, r1) == T_LADDER; l |= type_p(L, flags, c1, r1) == T_LADDER;
+    l |= type_p(L, flags, c0, r2) == T_LADDER; l |= type_p(L, flags, c1, r2) == T_LADDER;
+    return l;
+}
+// impl:252-257  a LADDER at (x +- 12, y + 0..51): rows floor(y/48), +1, floor((y+51)/48)
+__device__ __forceinline__ bool can_go_down(const LevelBlob &L, uint32_t flags, int px, int py) {
+    int c0 = pad_cell(px - 12), c1 = pad_cell(px + 12);
+    int r0 = pad_cell(py), r2 = pad_cell(py + 51), r1 = min(r0 + 1, r2);
+    bool l = false;
+    l |= type_p(L, flags, c0, r0) == T_LADDER; l |= type_p(L, flags, c1, r0) == T_LADDER;
+    l |= type_p(L, flags, c0, r1) == T_LADDER; l |= type_p(L, flags, c1, r1) == T_LADDER;
+    l |= type_p(L, flags, c0, r2) == T_LADDER; l |= type_p(L, flags, c1, r2) == T_LADDER;
+    return l;
+}
+// impl:259-281  no WALL / DOOR at (x -+ 16, y + {4, 44}); WALL and DOOR are the odd type codes
+__device__ __forceinline__ bool side_free(const LevelBlob &L, uint32_t flags, int x, int py) {
+    int c = pad_cell(x);
+    int t = type_p(L, flags, c, pad_cell(py + 4)) | type_p(L, flags, c, pad_cell(py + 44));
+    return (t & 1) == 0;
+}
+
+// objs:46-53 evaluated at (px, py + 24): integer form of sqrt(dx^2 + dy^2) < r
+__device__ __forceinline__ bool near_px(int px, int py, int ox, int oy, int r2) {
+    int dx = px - (ox + S / 2), dy = py - oy;
+    return dx * dx + dy * dy < r2;
+}
+
+__device__ __forceinline__ bool has_key(const LevelBlob &L, uint32_t f) { return ((f >> F_INBAG) & L.key_mask) != 0; }
+__device__ __forceinline__ bool has_gold(const LevelBlob &L, uint32_t f) { return ((f >> F_INBAG) & L.gold_mask) != 0; }
+
+// ---------------------------------------------------------------------------
+// trigger graph + INTERACT (rare: one tick per interact option) -- kept out of line
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool obj_value(const LevelBlob &L, uint32_t f, int o) {
+    int k = L.obj_kind[o], i = L.obj_idx[o];
+    int bit = (k == TG_DOOR) ? F_DOORS + i : (k == TG_HANDLE) ? F_HANDLES + i : F_BOLTS + i;
+    return (f >> bit) & 1u;
+}
+
+// set_val of door / handle / bolt (objs:145-149, :175-178, :231-235); returns true when the value
+// changed (the caller then runs process_trigger).  A handle redraws its angle (objs:127-131).
+template <bool TAPE, int NI>
+__device__ bool apply_val(Env<NI> &e, const LevelBlob &L, int o, bool v) {
+    int k = L.obj_kind[o], i = L.obj_idx[o];
+    int bit = (k == TG_DOOR) ? F_DOORS + i : (k == TG_HANDLE) ? F_HANDLES + i : F_BOLTS + i;
+    if ((bool)((e.flags >> bit) & 1u) == v) return false;
+    e.flags ^= 1u << bit;
+    if (k == TG_HANDLE) e.angles[(int64_t)i * e.n] = handle_angle(v, draw<TAPE>(e));
+    return true;
+}
+
+// set_val + recursive process_trigger (objs:76-94) as an explicit DFS.  `pt` is the set of
+// objects whose previously_triggered flag is raised (those on the DFS stack).
+template <bool TAPE, int NI>
+__device__ void set_val(Env<NI> &e, const LevelBlob &L, int o0, bool v0) {
+    if (!apply_val<TAPE>(e, L, o0, v0)) return;
+    uint8_t st_src[TG_MAX_OBJECTS], st_t[TG_MAX_OBJECTS];
+    int sp = 0;
+    uint32_t pt = 1u << o0;
+    st_src[0] = (uint8_t)(o0 | (v0 ? 128 : 0)); st_t[0] = 0; sp = 1;
+    while (sp > 0) {
+        int src = st_src[sp - 1], t = st_t[sp - 1];
+        bool pushed = false;
+        while (t < L.n_trigs) {
+            int cur = t++;
+            if (L.trig_src[cur] != src) continue;
+            int dst = L.trig_dst[cur] & 127; bool dv = L.trig_dst[cur] >> 7;
+            if (pt & (1u << dst)) continue;                       // objs:84 / :91
+            if (apply_val<TAPE>(e, L, dst, dv)) {
+                st_t[sp - 1] = (uint8_t)t;
+                pt |= 1u << dst;
+                st_src[sp] = (uint8_t)(dst | (dv ? 128 : 0)); st_t[sp] = 0; sp++;
+                pushed = true;
+                break;
+            }
+        }
+        if (!pushed) { pt &= ~(1u << (src & 127)); sp--; }         // objs:94
+    }
+}
+
+// impl:434-439: the first key in bag order leaves the bag and goes to cell (-1,-1)
+template <int NI>
+__device__ void drop_key(Env<NI> &e, const LevelBlob &L) {
+    int len = bag_len(e.flags);
+    uint32_t ord = e.flags >> F_BAGORD;
+    for (int j = 0; j < len; j++) {
+        int it = (ord >> (2 * j)) & 3;
+        if ((L.key_mask >> it) & 1) {
+            uint32_t low = ord & ((1u << (2 * j)) - 1u);
+            uint32_t high = (ord >> (2 * j + 2)) << (2 * j);
+            ord = (low | high) & 0xFFu;
+            e.flags = (e.flags & ~(0xFFu << F_BAGORD)) | (ord << F_BAGORD);
+            e.flags &= ~(1u << (F_INBAG + it));
+#pragma unroll
+            for (int q = 0; q < NI; q++) if (q == it) { e.ix[q] = -S; e.iy[q] = -S; }
+            return;
+        }
+    }
+}
+
+// impl:321-329
+template <bool TAPE, int NI>
+__device__ __noinline__ void interact(Env<NI> &e, const LevelBlob &L) {
+    for (int o = 0; o < L.n_objs; o++) {
+        int k = L.obj_kind[o], i = L.obj_idx[o];
+        if (k == TG_HANDLE) {
+            if (!near_px(e.px, e.py, L.handle_cx[i] * S, L.handle_cy[i] * S, 36 * 36)) continue;   // objs:115
+            bool up = (e.flags >> (F_HANDLES + i)) & 1u;
+            if (uniform_span(0.0, 1.0, draw<TAPE>(e)) <= 0.8) set_val<TAPE>(e, L, o, !up);       // objs:117-122
+            else e.angles[(int64_t)i * e.n] = handle_angle(up, draw<TAPE>(e));
+        } else if (k == TG_BOLT) {
+            if (!near_px(e.px, e.py, L.bolt_cx[i] * S, L.bolt_cy[i] * S, 24 * 24)) continue;
+            if (has_key(L, e.flags)) { set_val<TAPE>(e, L, o, false); drop_key(e, L); }          // impl:326-329
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// primitive tick  (impl:290-359)
+// ---------------------------------------------------------------------------
+// impl:361-366: int(round(uniform(-4,-2))) or int(round(uniform(2,4))), round-half-even
+template <bool TAPE, int NI>
+__device__ __forceinline__ int noisy(Env<NI> &e, bool negative) {
+    double u = draw<TAPE>(e);
+    return __double2int_rn(uniform_span(negative ? -4.0 : 2.0, 2.0, u));
+}
+
+template <bool TAPE, int NI>
+__device__ __forceinline__ void tick(Env<NI> &e, const LevelBlob &L, int act) {
+    int xd = 0, yd = 0;
+    e.total_actions++;
+    if (act == A_UP) {
+        if (can_go_up(L, e.flags, e.px, e.py)) yd = noisy<TAPE>(e, true);
+    } else if (act == A_DOWN) {
+        if (can_go_down(L, e.flags, e.px, e.py)) yd = noisy<TAPE>(e, false);
+    } else if (act == A_LEFT) {
+        if (side_free(L, e.flags, e.px - 16, e.py)) { xd = noisy<TAPE>(e, true); e.flags &= ~(1u << F_FACING); }
+    } else if (act == A_RIGHT) {
+        if (side_free(L, e.flags, e.px + 16, e.py)) { xd = noisy<TAPE>(e, false); e.flags |= 1u << F_FACING; }
+    } else if (act == A_JUMP) {
+        if (!can_go_down(L, e.flags, e.px, e.py) && up_clear(L, e.flags, e.px, e.py))
+            e.flags = set_ticker(e.flags, draw<TAPE>(e) > 0.25 ? 23 : 22);            // impl:316-319
+    } else if (act == A_INTERACT) {
+        interact<TAPE>(e, L);
+    }
+    int tk = ticker(e.flags);
+    if (tk > 0) {                                                                    // impl:331-334
+        if (up_clear(L, e.flags, e.px, e.py)) yd = -4;
+        e.flags = set_ticker(e.flags, tk - 1);
+    } else if (can_fall(L, e.flags, e.px, e.py)) {                                   // impl:335-337
+        yd = 4;
+    }
+    e.px += xd;                                                                      // impl:339
+    if (yd > 0 && can_fall(L, e.flags, e.px, e.py)) {                                // impl:341-346
+        do {
+            e.py++; yd--;
+            if (!can_fall(L, e.flags, e.px, e.py)) yd = 0;
+        } while (yd > 0);
+    } else {
+        e.py += yd;                                                                  // impl:348
+    }
+    // impl:350-354 pickups, item (= file) order
+    const int bx = (L.cw - 1) * S, by = (L.ch - 1) * S;
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+        if (i < L.n_items && near_px(e.px, e.py, e.ix[i], e.iy[i], 24 * 24)) {
+            int len = bag_len(e.flags);
+            e.ix[i] = bx - len * S; e.iy[i] = by;                                    // objs:34-38
+            e.flags |= 1u << (F_INBAG + i);
+            e.flags = (e.flags & ~(3u << (F_BAGORD + 2 * len))) | ((uint32_t)i << (F_BAGORD + 2 * len));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// option layer  (opts + opt:20-36)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int floordiv48(int v) { return (v >= 0) ? v / S : -((-v + S - 1) / S); }
+
+template <int NI>
+__device__ __forceinline__ void player_cell(const Env<NI> &e, int &cx, int &cy) {   // impl:441-445
+    cx = floordiv48(e.px); cy = floordiv48(e.py + S / 2);
+}
+
+// impl:402-409 is_object_at: handle / bolt / key / gold in the cell, or a *closed* door
+template <int NI>
+__device__ __forceinline__ bool object_at(const Env<NI> &e, const LevelBlob &L, int cx, int cy) {
+    int code = L.tiles[pad_idx(cy) * TSTRIDE + pad_idx(cx)];
+    bool r = (code & TC_STATIC_OBJ) != 0;
+    r |= (code & TC_HAS_DOOR) && ((e.flags >> (F_DOORS + (code >> 4))) & 1u);
+#pragma unroll
+    for (int i = 0; i < NI; i++)     // obj.cx/cy follow x/y (objs:34-44): trunc(x/48)
+        r |= (i < L.n_items) && (e.ix[i] / S == cx) && (e.iy[i] / S == cy);   // C '/' truncates like int(x / 48)
+    return r;
+}
+
+__device__ __forceinline__ bool closed_door_at(const LevelBlob &L, uint32_t flags, int cx, int cy) {  // impl:411-416
+    int code = L.tiles[pad_idx(cy) * TSTRIDE + pad_idx(cx)];
+    return (code & TC_HAS_DOOR) && ((flags >> (F_DOORS + (code >> 4))) & 1u);
+}
+
+// go_left (s=-1) / go_right (s=+1): can_run + target column.  opts:23-67 / opts:95-139
+template <int NI>
+__device__ bool walk_setup(const Env<NI> &e, const LevelBlob &L, int s, int &tcx) {
+    int pcx, pcy; player_cell(e, pcx, pcy);
+    const uint32_t f = e.flags;
+    bool ok = type_c(L, f, pcx, pcy) == T_OPEN && type_c(L, f, pcx, pcy + 1) != T_OPEN;
+    int xc = pcx + s;
+    for (int it = 0; it < TSTRIDE + 2; it++) {
+        bool tgt = type_c(L, f, xc, pcy - 1) == T_LADDER || type_c(L, f, xc, pcy + 1) == T_LADDER
+                || type_c(L, f, xc + s, pcy) == T_WALL || object_at(e, L, xc, pcy)
+                || closed_door_at(L, f, xc + s, pcy) || type_c(L, f, xc + s, pcy + 1) == T_OPEN;
+        ok = ok && type_c(L, f, xc, pcy) == T_OPEN && type_c(L, f, xc, pcy + 1) != T_OPEN;
+        if (tgt) { tcx = xc; return ok; }
+        xc += s;
+        if (xc < 0) return false;                       // opts:49-50 -> None -> not runnable
+    }
+    return false;
+}
+
+__device__ __forceinline__ bool landing(const LevelBlob &L, uint32_t f, int cx, int cy) {   // opts:281-287
+    return type_c(L, f, cx, cy) == T_OPEN && type_c(L, f, cx, cy + 1) == T_WALL;
+}
+
+// Evaluates can_run of option k (tg:83-89 / opt:22) and, for the options that walk to a
+// column, the target column.  err is set when the reference would raise (target None).
+template <int NI>
+__device__ bool option_setup(const Env<NI> &e, const LevelBlob &L, int k, int &tcx, bool &err) {
+    const uint32_t f = e.flags;
+    tcx = 0; err = false;
+    int pcx, pcy;
+    switch (k) {
+    case TG_GO_LEFT:  return walk_setup(e, L, -1, tcx);
+    case TG_GO_RIGHT: return walk_setup(e, L, +1, tcx);
+    case TG_UP_LADDER:   return can_go_up(L, f, e.px, e.py);          // opts:165-166
+    case TG_DOWN_LADDER: return can_go_down(L, f, e.px, e.py);        // opts:181-182
+    case TG_INTERACT: {                                               // opts:446-455
+        bool r = false;
+        for (int i = 0; i < L.n_handles; i++)
+            r |= near_px(e.px, e.py, L.handle_cx[i] * S, L.handle_cy[i] * S, 36 * 36);
+        if (has_key(L, f))
+            for (int i = 0; i < L.n_bolts; i++)
+                r |= near_px(e.px, e.py, L.bolt_cx[i] * S, L.bolt_cy[i] * S, 24 * 24);
+        return r;
+    }
+    case TG_DOWN_LEFT: case TG_DOWN_RIGHT: {                          // opts:199-221 / 394-416
+        int s = (k == TG_DOWN_LEFT) ? -1 : 1;
+        player_cell(e, pcx, pcy);
+        if (type_c(L, f, pcx + s, pcy) != T_OPEN || type_c(L, f, pcx + s, pcy + 1) != T_OPEN) return false;
+        tcx = pcx + s;
+        int yc = pcy + 1;
+        while (type_c(L, f, tcx, yc) == T_OPEN) { yc++; if (yc >= L.ch) { err = true; return false; } }
+        return true;
+    }
+    case TG_JUMP_LEFT: case TG_JUMP_RIGHT: {                          // opts:254-279 / 324-349
+        int s = (k == TG_JUMP_LEFT) ? -1 : 1;
+        player_cell(e, pcx, pcy);
+        if (type_c(L, f, pcx, pcy - 1) != T_OPEN || type_c(L, f, pcx + s, pcy - 1) != T_OPEN) return false;
+        if (landing(L, f, pcx + s, pcy - 1)) { tcx = pcx + s; return true; }
+        if (landing(L, f, pcx + 2 * s, pcy - 1)) { tcx = pcx + 2 * s; return true; }
+        return false;
+    }
+    }
+    return false;      // out-of-range action: the reference raises IndexError (tg:92); we report "not run"
+}
+
+// Runs option k to termination.  Returns the number of primitive ticks (0 = not runnable,
+// reference returns None); reward = -ticks - 4*[jump option]  (impl:15-16,356-359).
+template <bool TAPE, int NI>
+__device__ int run_option(Env<NI> &e, const LevelBlob &L, int k) {
+    int tcx; bool err;
+    if (!option_setup(e, L, k, tcx, err)) {
+        if (err) e.flags |= 1u << F_ERROR;
+        return 0;
+    }
+    const int tpx = tcx * S + S / 2;
+    const int s = (k == TG_GO_LEFT || k == TG_DOWN_LEFT || k == TG_JUMP_LEFT) ? -1 : 1;
+    int n = 0;
+    bool done = false;
+    do {
+        int act;
+        const bool al = abs(tpx - e.px) < 4;              // close_enough_*  (opts:69-72 ...)
+        if (k <= TG_GO_RIGHT) {                           // opts:74-85 / 146-157
+            done = al; act = (s < 0) ? A_LEFT : A_RIGHT;
+        } else if (k == TG_UP_LADDER) {                   // opts:168-173
+            done = !can_go_up(L, e.flags, e.px, e.py); act = done ? A_NOP : A_UP;
+        } else if (k == TG_DOWN_LADDER) {                 // opts:184-189
+            done = !can_go_down(L, e.flags, e.px, e.py); act = done ? A_NOP : A_DOWN;
+        } else if (k == TG_INTERACT) {                    // opts:457-460
+            done = true; act = A_INTERACT;
+        } else if (k <= TG_DOWN_RIGHT) {                  // opts:231-244 / 426-439
+            if (al) { done = !can_fall(L, e.flags, e.px, e.py); act = A_NOP; }
+            else act = (s < 0) ? A_LEFT : A_RIGHT;
+        } else {                                          // opts:297-314 / 367-384
+            if (n == 0) act = A_JUMP;
+            else if (al) { done = !can_fall(L, e.flags, e.px, e.py); act = A_NOP; }
+            else {
+                bool blocked = !side_free(L, e.flags, e.px + 16 * s, e.py);
+                bool grounded = !can_fall(L, e.flags, e.px, e.py);
+                bool rev = grounded && blocked;
+                act = ((s < 0) != rev) ? A_LEFT : A_RIGHT;
+            }
+        }
+        tick<TAPE>(e, L, act);
+        n++;
+        if (n >= TG_TICK_CAP && !done) { e.flags |= 1u << F_ERROR; break; }
+    } while (!done);
+    return n;
+}
+
+template <int NI>
+__device__ __forceinline__ uint32_t available_bits(const Env<NI> &e, const LevelBlob &L) {   // tg:83-89
+    uint32_t m = 0;
+    for (int k = 0; k < TG_NUM_OPTIONS; k++) {
+        int tcx; bool err;
+        if (option_setup(e, L, k, tcx, err)) m |= 1u << k;
+    }
+    return m;
+}
+
+// ---------------------------------------------------------------------------
+// reset  (impl:55-73, impl:168-178, objs:106-115) -- draws: one per handle (file order), then a gauss pair
+// ---------------------------------------------------------------------------
+template <bool TAPE, int NI>
+__device__ void reset_env(Env<NI> &e, const LevelBlob &L) {
+    e.flags = L.init_flags | (e.flags & (1u << F_ERROR));      // the error flag is sticky until tg_reset
+    for (int h = 0; h < L.n_handles; h++) {
+        bool up = (L.init_flags >> (F_HANDLES + h)) & 1u;
+        e.angles[(int64_t)h * e.n] = handle_angle(up, draw<TAPE>(e));
+    }
+#pragma unroll
+    for (int i = 0; i < NI; i++)
+        if (i < L.n_items) { e.ix[i] = L.item_cx[i] * S; e.iy[i] = L.item_cy[i] * S; }
+    // CPython random.gauss(mu, sigma): x2pi = random()*2pi; g2rad = sqrt(-2 log(1 - random()));
+    // z = cos(x2pi)*g2rad; gauss_next = sin(x2pi)*g2rad  (the second gauss() call consumes gauss_next)
+    double x2pi = __dmul_rn(draw<TAPE>(e), 6.283185307179586);
+    double g2rad = __dsqrt_rn(__dmul_rn(-2.0, log(__dsub_rn(1.0, draw<TAPE>(e)))));
+    double z0 = __dmul_rn(cos(x2pi), g2rad), z1 = __dmul_rn(sin(x2pi), g2rad);
+    int nx = (int)__dmul_rn(z0, 2.0);                            // int(gauss(0, 48/24))   impl:170
+    int ny = (int)fabs(__dmul_rn(z1, 48.0 / 36.0));              // int(abs(gauss(0, 48/36)))  impl:171
+    e.px = L.start_px + nx; e.py = L.start_py + ny;              // impl:176
+    if (L.start_px < 0) { e.px = 0; e.py = 0; }                  // impl:178 (level without a free cell)
+    e.total_actions = 0;
+}
+
+// ---------------------------------------------------------------------------
+// observation  (impl:368-378 + objs get_state): float64 arithmetic, stored as float32
+// ---------------------------------------------------------------------------
+template <int NI>
+__device__ __forceinline__ void write_obs(const Env<NI> &e, const LevelBlob &L, float *o, int obs_dim) {
+    const double W = (double)(L.cw * S), H = (double)(L.ch * S);
+    int k = 0;
+    o[k++] = (float)((double)e.px / W);
+    o[k++] = (float)((double)e.py / H);
+    for (int j = 0; j < L.n_objs; j++) {
+        int kind = L.obj_kind[j], i = L.obj_idx[j];
+        if (kind == TG_HANDLE) o[k++] = (float)e.angles[(int64_t)i * e.n];
+        else if (kind == TG_BOLT) o[k++] = ((e.flags >> (F_BOLTS + i)) & 1u) ? 1.0f : 0.0f;
+        else if (kind == TG_KEY || kind == TG_GOLD) {
+            int x = 0, y = 0;
+#pragma unroll
+            for (int q = 0; q < NI; q++) if (q == i) { x = e.ix[q]; y = e.iy[q]; }
+            o[k++] = (float)((double)x / W); o[k++] = (float)((double)y / H);
+        }
+    }
+    for (; k < obs_dim; k++) o[k] = 0.0f;
+}
+
+template <int NI>
+__device__ __forceinline__ bool is_done(const Env<NI> &e, const LevelBlob &L) {    // tg:95
+    return has_gold(L, e.flags) && floordiv48(e.py + S / 2) == 0;
+}
+
+// ---------------------------------------------------------------------------
+// packed state <-> registers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_xy(int x, int y) { return ((uint32_t)x & 0xFFFFu) | ((uint32_t)y << 16); }
+__device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xFFFFu); }
+__device__ __forceinline__ int hi16(uint32_t v) { return (int)(int16_t)(v >> 16); }
+
+template <int NI>
+__device__ __forceinline__ void load_env(Env<NI> &e, const BatchView &B, int64_t i, uint4 &acct) {
+    uint4 c = B.core[i];
+    acct = B.acct[i];
+    e.px = lo16(c.x); e.py = hi16(c.x); e.flags = c.y;
+    e.ix[0] = lo16(c.z); e.iy[0] = hi16(c.z);
+    if (NI > 1) { e.ix[1] = lo16(c.w); e.iy[1] = hi16(c.w); }
+    if (NI > 2) {
+        uint2 h = B.items23[i];
+        e.ix[2] = lo16(h.x); e.iy[2] = hi16(h.x);
+        if (NI > 3) { e.ix[3] = lo16(h.y); e.iy[3] = hi16(h.y); }
+    }
+    e.draws = acct.x; e.total_actions = acct.w;
+    e.blk = 0xFFFFFFFFu; e.w0 = e.w1 = e.w2 = e.w3 = 0;
+    e.key0 = B.seed_lo; e.key1 = B.seed_hi;
+    uint64_t id = (uint64_t)(B.first_env_id + i);
+    e.id_lo = (uint32_t)id; e.id_hi = (uint32_t)(id >> 32);
+    e.tape = B.tape ? B.tape + B.tape_off[i] : nullptr;
+    e.angles = B.angles + i; e.n = B.n;
+}
+
+template <int NI>
+__device__ __forceinline__ void store_env(const Env<NI> &e, const BatchView &B, int64_t i, uint4 acct) {
+    uint4 c;
+    c.x = pack_xy(e.px, e.py); c.y = e.flags;
+    c.z = pack_xy(e.ix[0], e.iy[0]);
+    c.w = (NI > 1) ? pack_xy(e.ix[1], e.iy[1]) : 0u;
+    B.core[i] = c;
+    if (NI > 2) {
+        uint2 h;
+        h.x = pack_xy(e.ix[2], e.iy[2]);
+        h.y = (NI > 3) ? pack_xy(e.ix[3], e.iy[3]) : 0u;
+        B.items23[i] = h;
+    }
+    acct.x = e.draws; acct.w = e.total_actions;
+    B.acct[i] = acct;
+}
+
+}  // namespace tg

@@ -1,0 +1,79 @@
+// Internal POD shared by host (level compiler in tg_capi.cu) and device code.
+#pragma once
+#include <stdint.h>
+#include <vector_types.h>
+#include "../../include/treasure_b200.h"
+
+namespace tg {
+
+constexpr int S = TG_CELL_PX;          // _scale.py:8-9
+constexpr int PAD = 3;                 // border of WALL cells around the grid in the tile table
+constexpr int TSTRIDE = 32;            // tile table is 32 x 32 bytes
+
+// effective cell types (after the door override, objs.py:246-253)
+enum : int { T_OPEN = 0, T_WALL = 1, T_LADDER = 2, T_DOOR = 3 };
+// tile-table byte: bits 0-1 base type, bit 2 static object (handle/bolt) in the cell,
+// bit 3 a door lives here, bits 4-6 its door index
+constexpr int TC_STATIC_OBJ = 4, TC_HAS_DOOR = 8;
+
+// primitive actions, _actions.py:7-13
+enum : int { A_NOP = 0, A_UP, A_DOWN, A_LEFT, A_RIGHT, A_JUMP, A_INTERACT };
+
+// flags word layout (per env)
+constexpr int F_FACING = 0;                       // 1 bit
+constexpr int F_TICKER = 1;                       // 5 bits
+constexpr int F_ERROR = 6;                        // 1 bit
+constexpr int F_DOORS = 7;                        // TG_MAX_DOORS bits, 1 = closed
+constexpr int F_HANDLES = F_DOORS + TG_MAX_DOORS; // 13, TG_MAX_HANDLES bits, 1 = up
+constexpr int F_BOLTS = F_HANDLES + TG_MAX_HANDLES; // 17, TG_MAX_BOLTS bits, 1 = locked
+constexpr int F_INBAG = F_BOLTS + TG_MAX_BOLTS;   // 20, TG_MAX_ITEMS bits
+constexpr int F_BAGORD = F_INBAG + TG_MAX_ITEMS;  // 24, TG_MAX_ITEMS x 2 bits: item index at bag position j
+static_assert(F_BAGORD + 2 * TG_MAX_ITEMS == 32, "flags word is exactly 32 bits");
+
+// One level, as staged in shared memory.  sizeof is a multiple of 16 (cp.async.bulk).
+struct alignas(16) LevelBlob {
+    uint8_t tiles[TSTRIDE * TSTRIDE];   // [(cy+PAD)*32 + (cx+PAD)]
+    int16_t cw, ch;
+    int16_t start_px, start_py;          // centre-x / top-y of the start cell before noise (impl:176)
+    uint8_t n_doors, n_handles, n_bolts, n_items, n_objs, n_trigs, obs_dim, key_mask; // key_mask: bit i = item i is a key
+    uint32_t init_flags;                 // facing=1, ticker=0, object bits from the level file
+    uint32_t gold_mask;                  // bit i = item i is gold
+    uint8_t obj_kind[TG_MAX_OBJECTS];    // file order (impl:127-163)
+    uint8_t obj_idx[TG_MAX_OBJECTS];     // index within its kind
+    uint8_t obj_obs[TG_MAX_OBJECTS];     // first obs slot of the object (impl:368-378), 255 = none
+    int8_t door_cx[8], door_cy[8];
+    int8_t handle_cx[4], handle_cy[4];
+    int8_t bolt_cx[4], bolt_cy[4];
+    int8_t item_cx[4], item_cy[4];       // initial cells
+    uint8_t handle_obj[4], bolt_obj[4], item_obj[4], door_obj[8];   // object (file-order) index of each
+    uint8_t trig_src[TG_MAX_TRIGGERS];   // object index | value << 7, file order (objs.py:65-71)
+    uint8_t trig_dst[TG_MAX_TRIGGERS];
+    float inv_w, inv_h;                  // unused by parity paths (obs divides in double)
+    uint32_t pad_[2];
+};
+static_assert(sizeof(LevelBlob) % 16 == 0, "LevelBlob must be a multiple of 16 bytes");
+
+// stats vector slots (tg_stats)
+enum : int { ST_EPISODES = 0, ST_SUCCESS, ST_RETURN, ST_EPSTEPS, ST_TICKS, ST_RAN, ST_STEPS, ST_ERRORS };
+
+// device-side description of one batch (passed by value to kernels)
+struct BatchView {
+    int64_t n;
+    int64_t first_env_id;
+    uint4 *core;          // [N]  x=pos(px | py<<16)  y=flags  z=item0 (x | y<<16)  w=item1
+    uint4 *acct;          // [N]  x=draws  y=ep_return  z=ep_steps  w=total_actions
+    uint2 *items23;       // [N]  items 2,3 (NULL when every level has <= 2 items)
+    double *angles;       // [TG_MAX_HANDLES][N]
+    const uint8_t *level_id;   // [N] or NULL
+    const LevelBlob *levels;   // [n_levels] in global memory
+    int32_t n_levels;
+    int32_t obs_dim;      // row stride of obs
+    int32_t max_steps;
+    int32_t auto_reset;
+    uint32_t seed_lo, seed_hi;
+    const double *tape;   // parity mode, or NULL
+    const int64_t *tape_off;
+    unsigned long long *stats;   // [8]
+};
+
+}  // namespace tg

@@ -1,0 +1,123 @@
+"""Single-environment Gym surface, drop-in for the reference's
+``gym_treasure_game/envs/treasure_game.py``: ``TreasureGame`` (``:54-114``) and
+``ObservationWrapper`` (``:38-51``) keep their names, argument meaning, return
+types and error behaviour; the work is done by the CUDA library through a
+one-env ``VectorTreasureGame`` (there is no CPU implementation).
+"""
+from __future__ import annotations
+
+import random
+
+import numpy as np
+import torch
+
+from ..level import BOLT, GOLD, HANDLE, KEY, Level
+from ..spaces import Box, Discrete
+from ..vector_env import OPTION_NAMES, VectorTreasureGame
+
+try:                                    # gym is optional (it is not installed in the build image)
+    import gym as _gym
+    _EnvBase, _WrapperBase = _gym.Env, _gym.Wrapper
+except Exception:                       # pragma: no cover - exercised where gym is absent
+    _gym = None
+
+    class _EnvBase:
+        pass
+
+    class _WrapperBase:
+        def __init__(self, env):
+            self.env = env
+
+        def __getattr__(self, name):
+            return getattr(self.env, name)
+
+        def reset(self, **kwargs):
+            return self.env.reset(**kwargs)
+
+        def step(self, action):
+            return self.env.step(action)
+
+        def render(self, mode="human"):
+            return self.env.render(mode=mode)
+
+        def close(self):
+            return self.env.close()
+
+
+class TreasureGame(_EnvBase):
+    metadata = {"render.modes": ["human", "rgb_array"]}          # treasure_game.py:55
+
+    def __init__(self, seed=None, device="cuda:0", level: Level = None):
+        """``seed`` selects the Philox stream; by default it is drawn from Python's global
+        ``random`` so that ``random.seed(k)`` before construction makes a run reproducible, as
+        with the reference (which has no seeding API of its own)."""
+        if seed is None:
+            seed = random.getrandbits(63)
+        self.level = level or Level.default()
+        # constructor = first reset (4 draws in the shipped level), treasure_game.py:67-70 -> impl:31-53
+        self._vec = VectorTreasureGame(1, device=device, seed=seed, auto_reset=False, levels=[self.level])
+        self.option_names = list(OPTION_NAMES)                    # impl:496
+        self.action_space = Discrete(len(OPTION_NAMES))          # treasure_game.py:73
+        self.observation_space = Box(np.float32(0.0), np.float32(1.0), shape=(self.level.obs_dim,))   # :75
+        self.viewer = None
+        self._actions = torch.zeros(1, dtype=torch.int32, device=self._vec.device)
+
+    # -- helpers ---------------------------------------------------------------
+    def _state_vector(self):
+        """float64 state vector exactly as impl:368-378 builds it (python list)."""
+        s = self._vec.get_state()
+        H, W = self.level.frame_size
+        pos = s["pos"][0].tolist()
+        angles = s["angles"][0].tolist()
+        bolts = s["bolts"][0].tolist()
+        items = s["items"][0].tolist()
+        v = [float(pos[0]) / W, float(pos[1]) / H]
+        h = b = it = 0
+        for kind, _, _, _ in self.level.objects:
+            if kind == HANDLE:
+                v.append(angles[h]); h += 1
+            elif kind == BOLT:
+                v.append(1.0 if bolts[b] else 0.0); b += 1
+            elif kind in (KEY, GOLD):
+                v += [float(items[it][0]) / W, float(items[it][1]) / H]; it += 1
+        return v
+
+    # -- gym API ------------------------------------------------------------------
+    def reset(self):
+        self._vec.reset()
+        return self._state_vector()
+
+    @property
+    def available_mask(self):
+        return self._vec.available_mask[0].cpu().numpy().astype(np.int64)   # treasure_game.py:89
+
+    def step(self, action):
+        action = range(len(OPTION_NAMES))[action]     # IndexError on a bad id, like option_list[action] (:92)
+        self._actions[0] = action
+        _, reward, done, info = self._vec.step(self._actions)
+        ran = bool(info["ran"][0])
+        r = int(reward[0]) if ran else None           # option.run() returns None when it cannot run (_option.py:22-23)
+        return self._state_vector(), r, bool(info["terminated"][0]), {}
+
+    def render(self, mode="human"):
+        rgb = self._vec.render("rgb_array")[0].cpu().numpy()
+        if mode == "rgb_array":
+            return rgb
+        raise NotImplementedError("render('human') needs gym's SimpleImageViewer and a display; use mode='rgb_array'")
+
+    def close(self):
+        self._vec.close()
+
+
+class ObservationWrapper(_WrapperBase):
+    """RGB observations (treasure_game.py:38-51): the vector state moves to info['world_state']."""
+
+    def reset(self, **kwargs):
+        self.env.reset(**kwargs)
+        return self.env.render(mode="rgb_array")
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(action)
+        info["world_state"] = obs
+        screen = self.env.render(mode="rgb_array")
+        return screen, reward, done, info

@@ -1,0 +1,287 @@
+"""``VectorTreasureGame``: N Treasure Game environments stepped by one CUDA kernel.
+
+Host-side mirror of the reference's Gym surface (``treasure_game.py:54-114``)
+for a batch: ``reset`` / ``step`` / ``available_mask`` / ``render`` keep the
+reference's names and argument meaning; results are PyTorch CUDA tensors that
+view buffers owned by this object (they are overwritten by the next call --
+clone them if they must survive).  All compute happens in
+``libtreasure_b200.so``; torch only provides device memory and the stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import TgLevelInfo, TgObject, TgStateView, TgTrigger, TreasureError, check
+from .level import Level
+from .spaces import Box, Discrete
+from . import sprites as _sprites
+
+OPTION_NAMES = ["go_left_option", "go_right_option", "up_ladder_option", "down_ladder_option",
+                "interact_option", "down_left_option", "down_right_option", "jump_left_option",
+                "jump_right_option"]                      # _treasure_game_impl.py:495-496
+STAT_NAMES = ["episodes", "successes", "return_sum", "episode_steps_sum", "primitive_ticks",
+              "runnable_steps", "gym_steps", "errors"]
+
+
+class CompiledLevel:
+    """A ``Level`` compiled by ``tg_level_create`` (+ render assets)."""
+
+    def __init__(self, level: Level, with_sprites: bool = True):
+        L = _lib.lib()
+        self.level = level
+        tiles = "".join(level.tiles).encode("latin-1")
+        objs = (TgObject * max(len(level.objects), 1))(*[TgObject(k, cx, cy, int(f)) for k, cx, cy, f in level.objects])
+        trg = (TgTrigger * max(len(level.triggers), 1))(*[TgTrigger(a, b, int(c), d, e, int(f))
+                                                         for a, b, c, d, e, f in level.triggers])
+        h = C.c_void_p()
+        check(L.tg_level_create(tiles, level.cw, level.ch, objs, len(level.objects), trg, len(level.triggers), C.byref(h)))
+        self.handle = h
+        self.info = TgLevelInfo()
+        check(L.tg_level_get_info(self.handle, C.byref(self.info)))
+        if with_sprites:
+            atlas = np.ascontiguousarray(_sprites.dynamic_atlas())
+            bg = np.ascontiguousarray(_sprites.compose_background(level))
+            check(L.tg_level_set_sprites(self.handle, atlas.ctypes.data_as(C.c_void_p), bg.ctypes.data_as(C.c_void_p)))
+            check(L.tg_level_get_info(self.handle, C.byref(self.info)))
+            self.background = bg
+
+    def __del__(self):
+        try:
+            h = getattr(self, "handle", None)
+            if h and _lib._lib is not None:
+                _lib._lib.tg_level_destroy(h)
+                self.handle = None
+        except Exception:      # interpreter shutdown
+            pass
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class VectorTreasureGame:
+    metadata = {"render.modes": ["rgb_array"]}
+
+    def __init__(self, num_envs: int, device="cuda:0", seed: int = 0, max_episode_steps: int = 0,
+                 auto_reset: bool = True, levels: Optional[Sequence[Level]] = None,
+                 level_ids: Optional[Sequence[int]] = None, first_env_id: int = 0, render: bool = True):
+        if not torch.cuda.is_available():
+            raise TreasureError("VectorTreasureGame needs a CUDA device; there is no CPU fallback")
+        self._L = _lib.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise TreasureError("device must be a CUDA device, got %s" % device)
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", dev_index)
+        self.num_envs = int(num_envs)
+        self.levels = list(levels) if levels else [Level.default()]
+        self._compiled = [CompiledLevel(lv, with_sprites=render) for lv in self.levels]
+        arr = (C.c_void_p * len(self._compiled))(*[c.handle for c in self._compiled])
+        ids = None
+        if level_ids is not None:
+            ids = np.ascontiguousarray(level_ids, dtype=np.uint8)
+            if ids.shape != (self.num_envs,):
+                raise ValueError("level_ids must have one entry per env")
+        h = C.c_void_p()
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            check(self._L.tg_create(arr, len(self._compiled), None if ids is None else ids.ctypes.data_as(C.c_void_p),
+                                    self.num_envs, int(first_env_id), dev_index, int(seed) & (2 ** 64 - 1),
+                                    int(max_episode_steps), int(bool(auto_reset)), C.byref(h)))
+        self._h = h
+        self.level_ids = ids
+        self.obs_dim = int(self._L.tg_obs_dim(self._h))
+        self.frame_shape = (self.levels[0].frame_size[0], self.levels[0].frame_size[1], 3)
+        self.max_episode_steps, self.auto_reset = int(max_episode_steps), bool(auto_reset)
+        self.option_names = list(OPTION_NAMES)
+        self.single_action_space = Discrete(len(OPTION_NAMES))                       # treasure_game.py:73
+        self.single_observation_space = Box(np.float32(0.0), np.float32(1.0), shape=(self.obs_dim,))   # :75
+        self.action_space, self.observation_space = self.single_action_space, self.single_observation_space
+        n, d = self.num_envs, self.device
+        self._obs = torch.empty((n, self.obs_dim), dtype=torch.float32, device=d)
+        self._reward = torch.empty((n,), dtype=torch.float32, device=d)
+        self._done = torch.empty((n,), dtype=torch.uint8, device=d)
+        self._ran = torch.empty((n,), dtype=torch.uint8, device=d)
+        self._avail = None
+        self._mask = None
+        self._stats = torch.zeros((8,), dtype=torch.int64, device=d)
+        self._tape = None
+        self._host = None
+
+    # ------------------------------------------------------------------ utils
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.tg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ gym surface
+    def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``TreasureGame.reset`` (treasure_game.py:78-81) for every env, or for ``mask != 0``."""
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        check(self._L.tg_reset(self._h, _ptr(mask), _ptr(self._obs), self._stream()))
+        return self._obs
+
+    def step(self, actions: torch.Tensor, want_available: bool = False):
+        """``TreasureGame.step`` (treasure_game.py:91-96).  Returns ``(obs, reward, done, info)``:
+        obs (N, obs_dim) f32, reward (N,) f32 -- 0 where the option was not runnable (the
+        reference returns ``None``; see ``info['ran']``), done (N,) bool, info with
+        ``ran``, ``terminated``, ``truncated`` (and ``available`` (N,) int16 bit masks)."""
+        if actions.dtype != torch.int32 or actions.device != self.device or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
+        if actions.shape != (self.num_envs,):
+            raise ValueError("actions must have shape (%d,)" % self.num_envs)
+        if want_available and self._avail is None:
+            self._avail = torch.empty((self.num_envs,), dtype=torch.int16, device=self.device)
+        check(self._L.tg_step(self._h, _ptr(actions), _ptr(self._obs), _ptr(self._reward), _ptr(self._done),
+                              _ptr(self._ran), _ptr(self._avail) if want_available else None, self._stream()))
+        done = self._done != 0
+        info = {"ran": self._ran.bool(), "terminated": (self._done & _lib.DONE_TERMINATED) != 0,
+                "truncated": (self._done & _lib.DONE_TRUNCATED) != 0}
+        if want_available:
+            info["available"] = self._avail
+        return self._obs, self._reward, done, info
+
+    def step_raw(self, actions: torch.Tensor):
+        """Hot-loop variant: no tensor post-processing; returns the raw output buffers
+        ``(obs, reward, done_bits, ran)``."""
+        check(self._L.tg_step(self._h, _ptr(actions), _ptr(self._obs), _ptr(self._reward), _ptr(self._done),
+                              _ptr(self._ran), None, self._stream()))
+        return self._obs, self._reward, self._done, self._ran
+
+    def make_host_buffers(self):
+        """Pinned host buffers for ``step_host`` (actions in; obs, reward, done, ran out)."""
+        n = self.num_envs
+        self._host = dict(
+            actions=torch.empty((n,), dtype=torch.int32).pin_memory(),
+            obs=torch.empty((n, self.obs_dim), dtype=torch.float32).pin_memory(),
+            reward=torch.empty((n,), dtype=torch.float32).pin_memory(),
+            done=torch.empty((n,), dtype=torch.uint8).pin_memory(),
+            ran=torch.empty((n,), dtype=torch.uint8).pin_memory())
+        return self._host
+
+    def step_host(self, host: Optional[Dict[str, torch.Tensor]] = None):
+        """End-to-end step through ``tg_step_host``: host actions in, host obs/reward/done/ran out,
+        with the copies and the final synchronisation inside the call."""
+        host = host or self._host or self.make_host_buffers()
+        check(self._L.tg_step_host(self._h, _ptr(host["actions"]), _ptr(host["obs"]), _ptr(host["reward"]),
+                                   _ptr(host["done"]), _ptr(host["ran"]), self._stream()))
+        return host
+
+    @property
+    def available_mask(self) -> torch.Tensor:
+        """``TreasureGame.available_mask`` (treasure_game.py:83-89): (N, 9) uint8."""
+        if self._mask is None:
+            self._mask = torch.empty((self.num_envs, 9), dtype=torch.uint8, device=self.device)
+        check(self._L.tg_available_mask(self._h, _ptr(self._mask), self._stream()))
+        return self._mask
+
+    def render(self, mode: str = "rgb_array", first: int = 0, count: Optional[int] = None,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``TreasureGame.render('rgb_array')`` (treasure_game.py:98-104): (count, H, W, 3) uint8."""
+        if mode != "rgb_array":
+            raise NotImplementedError("only mode='rgb_array' is supported (no on-screen viewer)")
+        count = self.num_envs - first if count is None else count
+        if out is None:
+            out = torch.empty((count,) + self.frame_shape, dtype=torch.uint8, device=self.device)
+        elif out.shape != (count,) + self.frame_shape or out.dtype != torch.uint8 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous uint8 tensor of shape %s" % ((count,) + self.frame_shape,))
+        check(self._L.tg_render(self._h, first, count, _ptr(out), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ state access / parity hooks
+    def get_state(self) -> Dict[str, torch.Tensor]:
+        n, d = self.num_envs, self.device
+        t = dict(
+            pos=torch.empty((n, 2), dtype=torch.int32, device=d), misc=torch.empty((n, 4), dtype=torch.int32, device=d),
+            doors=torch.empty((n, _lib.MAX_DOORS), dtype=torch.uint8, device=d),
+            handles=torch.empty((n, _lib.MAX_HANDLES), dtype=torch.uint8, device=d),
+            bolts=torch.empty((n, _lib.MAX_BOLTS), dtype=torch.uint8, device=d),
+            angles=torch.empty((n, _lib.MAX_HANDLES), dtype=torch.float64, device=d),
+            items=torch.empty((n, _lib.MAX_ITEMS, 2), dtype=torch.int32, device=d),
+            bag=torch.empty((n, _lib.MAX_ITEMS), dtype=torch.int32, device=d),
+            acct=torch.empty((n, 3), dtype=torch.int64, device=d))
+        v = TgStateView(**{k: t[k].data_ptr() for k in t})
+        check(self._L.tg_get_state(self._h, C.byref(v), self._stream()))
+        return t
+
+    def set_state(self, state: Dict[str, torch.Tensor]) -> None:
+        dt = dict(pos=torch.int32, misc=torch.int32, doors=torch.uint8, handles=torch.uint8, bolts=torch.uint8,
+                  angles=torch.float64, items=torch.int32, bag=torch.int32, acct=torch.int64)
+        keep = {k: state[k].to(device=self.device, dtype=dt[k]).contiguous() for k in state}
+        v = TgStateView(**{k: keep[k].data_ptr() for k in keep})
+        check(self._L.tg_set_state(self._h, C.byref(v), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def snapshot(self, i: int = 0, state: Optional[Dict[str, torch.Tensor]] = None) -> dict:
+        """State of env ``i`` in the dict layout of the oracle snapshots (tests)."""
+        s = state or self.get_state()
+        lv = self.levels[int(self.level_ids[i]) if self.level_ids is not None else 0]
+        info = self._compiled[int(self.level_ids[i]) if self.level_ids is not None else 0].info
+        c = {k: v[i].cpu().numpy() for k, v in s.items()}
+        ni = info.n_items
+        return dict(
+            px=int(c["pos"][0]), py=int(c["pos"][1]), facing=int(c["misc"][0]), ticker=int(c["misc"][1]),
+            doors=[int(v) for v in c["doors"][: info.n_doors]], handles_up=[int(v) for v in c["handles"][: info.n_handles]],
+            angles=[float(v) for v in c["angles"][: info.n_handles]], bolts=[int(v) for v in c["bolts"][: info.n_bolts]],
+            items=[(int(x), int(y), int(np.trunc(x / 48)), int(np.trunc(y / 48))) for x, y in c["items"][:ni]],
+            bag=[int(v) for v in c["bag"][:ni] if v >= 0], total_actions=int(c["misc"][2]))
+
+    def set_draw_tape(self, tapes: Optional[Sequence[Sequence[float]]]) -> None:
+        """Parity mode: env i consumes ``tapes[i]`` (uniform draws recorded from the reference)
+        instead of its Philox stream; ``None`` switches back.  Draw indices restart at 0."""
+        if tapes is None:
+            check(self._L.tg_set_draw_tape(self._h, None, None, self._stream()))
+            self._tape = None
+            return
+        if len(tapes) != self.num_envs:
+            raise ValueError("one tape per env")
+        off = np.zeros(self.num_envs + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(t) for t in tapes])
+        flat = np.concatenate([np.asarray(t, dtype=np.float64) for t in tapes]) if off[-1] else np.zeros(1)
+        self._tape = (torch.from_numpy(flat).to(self.device), torch.from_numpy(off).to(self.device))
+        check(self._L.tg_set_draw_tape(self._h, _ptr(self._tape[0]), _ptr(self._tape[1]), self._stream()))
+
+    # ------------------------------------------------------------------ statistics
+    def stats_tensor(self) -> torch.Tensor:
+        """Local int64[8] statistics vector (device); see ``STAT_NAMES``."""
+        check(self._L.tg_stats(self._h, _ptr(self._stats), self._stream()))
+        return self._stats
+
+    def stats(self, all_reduce: bool = False) -> Dict[str, int]:
+        """Episode statistics; with ``all_reduce`` summed over the ranks of the default
+        ``torch.distributed`` group (the only collective of this path)."""
+        t = self.stats_tensor().clone()
+        if all_reduce:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return dict(zip(STAT_NAMES, (int(v) for v in t.cpu())))
+
+    def clear_stats(self) -> None:
+        check(self._L.tg_stats_clear(self._h, self._stream()))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.tg_launch_count(self._h))
+
+
+def shard_range(total_envs: int, rank: int, world_size: int):
+    """Contiguous env-id range owned by ``rank``: [lo, hi)."""
+    base, rem = divmod(total_envs, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

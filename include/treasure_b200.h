@@ -1,0 +1,181 @@
+/*
+ * treasure_b200 -- C ABI of the B200-native batched Treasure Game simulator.
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference
+ * (sd-james/gym-treasure-game) is pure Python and has no FFI of its own; the
+ * interface user code programs against is the Gym protocol of
+ *   gym_treasure_game/envs/treasure_game.py:54-114  (TreasureGame.reset/step/
+ *   available_mask/render) and :38-51 (ObservationWrapper),
+ * backed by _treasure_game_impl/_treasure_game_impl.py:19-481 (_TreasureGameImpl)
+ * and the option layer (_option.py:20-36, _move_options.py:16-460).  Each entry
+ * point below names the reference function(s) it replaces; INTEGRATION.md shows
+ * the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no CUDA or torch types (streams are
+ *     passed as `void*` holding a cudaStream_t / CUstream; NULL = legacy stream).
+ *   - Pointers marked DEV are device pointers on the env's device, owned by the
+ *     caller; HOST pointers are host memory (pinned memory makes the *_host
+ *     calls asynchronous up to their final synchronisation).
+ *   - Every call returns 0 on success or a negative tg_status; the message is
+ *     available from tg_last_error() (thread-local).  No exceptions, no aborts.
+ *   - A tg_env is bound to one device and is not thread-safe; distinct tg_env
+ *     objects are independent.  All device work is enqueued on the given stream
+ *     and is asynchronous unless stated otherwise.
+ *   - There is NO CPU fallback: every compute entry point fails with
+ *     TG_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef TREASURE_B200_H
+#define TREASURE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TG_ABI_VERSION 1
+
+/* compile-time limits of one level (the shipped level uses 3/2/1/2 objects on a 14x13 grid) */
+#define TG_MAX_DOORS   6
+#define TG_MAX_HANDLES 4
+#define TG_MAX_BOLTS   3
+#define TG_MAX_ITEMS   4      /* keys + gold coins */
+#define TG_MAX_OBJECTS 16
+#define TG_MAX_TRIGGERS 32
+#define TG_MAX_GRID    26     /* cells per side */
+#define TG_MAX_LEVELS  8      /* distinct layouts in one batch */
+#define TG_NUM_OPTIONS 9      /* _treasure_game_impl.py:495 */
+#define TG_TICK_CAP    4096   /* primitive ticks per option before the env is flagged (reference would hang) */
+
+#define TG_FRAME_CHANNELS 3
+#define TG_CELL_PX 48         /* _scale.py:8-9 */
+
+typedef enum {
+    TG_OK = 0,
+    TG_ERR_ARG = -1,          /* bad argument / level outside the limits above */
+    TG_ERR_CUDA = -2,         /* CUDA runtime error or no device */
+    TG_ERR_STATE = -3,        /* call not valid in this state (e.g. render without sprites) */
+    TG_ERR_NOMEM = -4
+} tg_status;
+
+/* object kinds, in the spelling of domain-objects.txt (_treasure_game_impl.py:127-163) */
+enum { TG_DOOR = 0, TG_HANDLE = 1, TG_KEY = 2, TG_BOLT = 3, TG_GOLD = 4 };
+
+/* option ids == gym action ids (_treasure_game_impl.py:495) */
+enum { TG_GO_LEFT = 0, TG_GO_RIGHT, TG_UP_LADDER, TG_DOWN_LADDER, TG_INTERACT,
+       TG_DOWN_LEFT, TG_DOWN_RIGHT, TG_JUMP_LEFT, TG_JUMP_RIGHT };
+
+/* done byte written by tg_step */
+#define TG_DONE_TERMINATED 1  /* gold in bag and player in row 0 (treasure_game.py:95) */
+#define TG_DONE_TRUNCATED  2  /* max_episode_steps reached (no reference counterpart) */
+
+typedef struct { int32_t kind, cx, cy, flag; } tg_object;          /* flag: closed / up / locked */
+typedef struct { int32_t src_kind, src_index, src_value,
+                         dst_kind, dst_index, dst_value; } tg_trigger; /* one line of domain-interactions.txt */
+
+typedef struct tg_level tg_level;
+typedef struct tg_env tg_env;
+
+typedef struct {
+    int32_t cw, ch;                     /* grid size in cells */
+    int32_t n_doors, n_handles, n_bolts, n_items, n_objects, n_triggers;
+    int32_t obs_dim;                    /* 2 + handles + bolts + 2*items (impl:368-378) */
+    int32_t start_cx, start_cy;         /* first non-wall cell, row-major (impl:173-176) */
+    int32_t frame_w, frame_h;           /* 48*cw, 48*ch */
+    int32_t has_sprites;
+} tg_level_info;
+
+/* Flat, unpacked view of the per-env state; every pointer is DEV and may be NULL.
+ * Strides are the TG_MAX_* constants regardless of the level. */
+typedef struct {
+    int32_t *pos;       /* [N][2]  playerx, playery                                  */
+    int32_t *misc;      /* [N][4]  facing_right, jump_ticker, total_actions, draws   */
+    uint8_t *doors;     /* [N][TG_MAX_DOORS]    closed                               */
+    uint8_t *handles;   /* [N][TG_MAX_HANDLES]  up                                   */
+    uint8_t *bolts;     /* [N][TG_MAX_BOLTS]    locked                               */
+    double  *angles;    /* [N][TG_MAX_HANDLES]                                       */
+    int32_t *items;     /* [N][TG_MAX_ITEMS][2] x, y in pixels                       */
+    int32_t *bag;       /* [N][TG_MAX_ITEMS]    item index per bag slot, -1 = empty  */
+    int64_t *acct;      /* [N][3]  episode return, episode steps, error flag         */
+} tg_state_view;
+
+const char *tg_last_error(void);
+int tg_abi_version(void);
+/* number of usable CUDA devices (0 when there is none); never fails */
+int tg_device_count(void);
+
+/* ---- level: replaces the parsers' output (impl:180-202 tiles, impl:119-166 objects,
+ *      impl:75-117 triggers).  HOST data, copied.  tiles: ch rows of cw chars, ' ' '/' 'L'. */
+int tg_level_create(const uint8_t *tiles, int32_t cw, int32_t ch,
+                    const tg_object *objs, int32_t n_objs,
+                    const tg_trigger *trigs, int32_t n_trigs, tg_level **out);
+int tg_level_get_info(const tg_level *lv, tg_level_info *out);
+/* Render assets (replaces _treasure_game_drawer.py:59-134 sprite loading and the
+ * static tile layer of draw_domain :140-152).  HOST data, copied.
+ *   background_rgb : frame_h*frame_w*3 bytes, the precomposed tile layer
+ *   sprites_rgba   : TG_NUM_SPRITES sprites of 48*48*4 bytes (order: tg_sprite_id) */
+enum { TG_SPR_DOOR_CLOSED = 0, TG_SPR_DOOR_OPEN, TG_SPR_KEY, TG_SPR_GOLD, TG_SPR_BOLT_OPEN,
+       TG_SPR_BOLT_LOCKED, TG_SPR_HANDLE_BASE, TG_SPR_HERO_RIGHT, TG_SPR_HERO_LEFT, TG_NUM_SPRITES };
+int tg_level_set_sprites(tg_level *lv, const uint8_t *sprites_rgba, const uint8_t *background_rgb);
+void tg_level_destroy(tg_level *lv);
+
+/* ---- batch of environments: replaces TreasureGame.__init__ (treasure_game.py:63-76).
+ * level_ids: HOST, num_envs bytes selecting levels[level_ids[i]], or NULL (all level 0).
+ * Env i uses Philox stream (seed, first_env_id + i) so results do not depend on how a
+ * population is sharded over devices.  max_episode_steps 0 = no time limit.
+ * The envs are created reset (constructor draws, impl:31-53). */
+int tg_create(const tg_level *const *levels, int32_t n_levels, const uint8_t *level_ids,
+              int64_t num_envs, int64_t first_env_id, int32_t device, uint64_t seed,
+              int32_t max_episode_steps, int32_t auto_reset, tg_env **out);
+void tg_destroy(tg_env *env);
+int64_t tg_num_envs(const tg_env *env);
+int32_t tg_obs_dim(const tg_env *env);      /* max over the batch's levels */
+
+/* TreasureGame.reset (treasure_game.py:78-81 -> impl:55-73).  mask DEV [N] (non-zero = reset) or NULL = all.
+ * obs DEV [N][obs_dim] float32 or NULL. */
+int tg_reset(tg_env *env, const uint8_t *mask, float *obs, void *stream);
+
+/* TreasureGame.step (treasure_game.py:91-96 -> _option.py:20-36 -> impl:290-359).
+ *   actions DEV [N] int32 option ids; obs DEV [N][obs_dim] f32; reward DEV [N] f32 (0 where the
+ *   option was not runnable -- the reference returns None there, see `ran`); done DEV [N] u8
+ *   (TG_DONE_* bits); ran DEV [N] u8 or NULL; avail DEV [N] u16 or NULL: 9-bit available mask of
+ *   the state *after* the step (bit k = option k runnable; treasure_game.py:83-89).
+ * With auto_reset, an env whose episode ended is reset inside the call and obs holds the first
+ * observation of the new episode. */
+int tg_step(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done,
+            uint8_t *ran, uint16_t *avail, void *stream);
+
+/* Same, with HOST buffers (pinned recommended): copies actions in, runs the step, copies
+ * obs/reward/done(/ran) out and synchronises the stream.  Any output may be NULL. */
+int tg_step_host(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done,
+                 uint8_t *ran, void *stream);
+
+/* TreasureGame.available_mask (treasure_game.py:83-89).  mask DEV [N][9] u8. */
+int tg_available_mask(tg_env *env, uint8_t *mask, void *stream);
+
+/* TreasureGame.render('rgb_array') (treasure_game.py:98-104 -> drawer.draw_domain :136-163).
+ * frames DEV [count][frame_h][frame_w][3] u8 for envs first .. first+count-1. */
+int tg_render(tg_env *env, int64_t first, int64_t count, uint8_t *frames, void *stream);
+
+/* State save / restore on the SoA (test hook; superset of impl:368-378 / :447-481). */
+int tg_get_state(tg_env *env, const tg_state_view *out, void *stream);
+int tg_set_state(tg_env *env, const tg_state_view *in, void *stream);
+
+/* Parity mode: uniform draws come from tape[offsets[i] + draw_index_i] instead of Philox.
+ * Both DEV, must stay valid until replaced; (NULL, NULL) returns to Philox.  Resets draw indices to 0. */
+int tg_set_draw_tape(tg_env *env, const double *tape, const int64_t *offsets, void *stream);
+
+/* Episode statistics accumulated on the device since creation (or the last tg_stats_clear):
+ * out8 DEV int64[8] = episodes, successes, sum return, sum episode steps, primitive ticks,
+ * runnable steps, gym steps, errors.  This is the vector the host all-reduces over ranks. */
+int tg_stats(tg_env *env, int64_t *out8, void *stream);
+int tg_stats_clear(tg_env *env, void *stream);
+
+/* how many kernels this library has launched on behalf of `env` (bench bookkeeping) */
+int64_t tg_launch_count(const tg_env *env);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TREASURE_B200_H */

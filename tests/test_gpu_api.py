@@ -1,0 +1,56 @@
+"""GPU: the reference-facing single-env Gym surface (treasure_game.py:38-114) served by the CUDA path."""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_readme_loop_and_none_reward():
+    import gym_treasure_game_b200 as tgb
+    random.seed(0)
+    env = tgb.make("treasure_game-v0")
+    assert env.action_space.n == 9 and env.observation_space.shape == (9,)
+    s = env.reset()
+    assert isinstance(s, list) and len(s) == 9 and all(isinstance(v, float) for v in s)
+    assert env.available_mask.tolist() == [0, 0, 0, 1, 0, 0, 0, 0, 0]
+    s2, r, done, info = env.step(0)                                        # go_left is not runnable at the start
+    assert r is None and done is False and info == {} and s2 == s
+    s3, r, done, _ = env.step(3)                                           # down the first ladder
+    assert isinstance(r, int) and r < 0 and s3 != s
+    for episode in range(2):                                               # README.md:40-48
+        env.reset()
+        for _ in range(100):
+            _, reward, done, _ = env.step(env.action_space.sample())
+            assert reward is None or reward < 0
+            if done:
+                break
+    with pytest.raises(IndexError):
+        env.step(9)
+    env.close()
+
+
+def test_observation_wrapper():
+    from gym_treasure_game_b200.envs import ObservationWrapper, TreasureGame
+    env = ObservationWrapper(TreasureGame(seed=5))
+    obs = env.reset()
+    assert obs.shape == (624, 672, 3) and obs.dtype == np.uint8
+    frame, r, done, info = env.step(3)
+    assert frame.shape == (624, 672, 3) and len(info["world_state"]) == 9
+    assert (frame != obs).any()
+    env.close()
+
+
+def test_seed_reproducibility():
+    from gym_treasure_game_b200.envs import TreasureGame
+    outs = []
+    for _ in range(2):
+        random.seed(123)
+        e = TreasureGame()
+        tr = [e.reset()]
+        for a in [3, 0, 4, 4, 1, 1, 3]:
+            tr.append(e.step(a))
+        outs.append(tr)
+        e.close()
+    assert outs[0] == outs[1]

@@ -1,0 +1,178 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against
+(a) the reference-generated golden trajectories with the reference's uniform
+draws injected, and (b) the C oracle in Philox mode on seeded batches.
+Integer/boolean/index state is compared bit-exactly; float64 handle angles
+bit-exactly; float32 observations against the float64 oracle value rounded to
+float32 (tolerance stated by north_star: 1e-6 relative -- we get 0)."""
+import numpy as np
+import pytest
+import torch
+
+import c_oracle
+import py_oracle as po
+from conftest import golden_files, golden_level, load_golden, norm_snap
+from gpu_util import assert_state_equal, assert_step_equal, product_level
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def VTG():
+    from gym_treasure_game_b200 import VectorTreasureGame
+    return VectorTreasureGame
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-8])
+def test_cuda_replays_reference_golden(VTG, path):
+    rec = load_golden(path)
+    lvt = golden_level(rec)
+    env = VTG(1, seed=1, auto_reset=False, levels=[product_level(lvt)], render=False)
+    env.set_draw_tape([rec["tape"]])
+    env.reset()                                   # the reference constructor's draws
+    obs = env.reset()                             # TreasureGame.reset()
+    assert env.snapshot(0) == norm_snap(rec["init"]["snap"])
+    np.testing.assert_array_equal(obs[0].cpu().numpy(), np.asarray(rec["init"]["obs"], dtype=np.float32))
+    a = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for t, st in enumerate(rec["steps"]):
+        assert env.available_mask[0].tolist() == st["mask"], t
+        a[0] = st["a"]
+        obs, rew, done, info = env.step(a, want_available=True)
+        state = env.get_state()
+        assert bool(info["ran"][0]) == (st["r"] is not None), t
+        assert int(rew[0]) == (st["r"] or 0), t
+        assert bool(info["terminated"][0]) == st["done"], t
+        np.testing.assert_array_equal(obs[0].cpu().numpy(), np.asarray(st["obs"], dtype=np.float32), err_msg=str(t))
+        assert env.snapshot(0, state) == norm_snap(st["snap"]), t          # incl. float64 angles, bag order
+        assert int(state["misc"][0, 3]) == st["draws"], t                   # draws consumed
+        if t + 1 < len(rec["steps"]):                                       # avail-after-step == next mask
+            nxt = rec["steps"][t + 1]["mask"]
+            assert [(int(info["available"][0]) >> k) & 1 for k in range(9)] == nxt, t
+    env.close()
+
+
+@pytest.mark.parametrize("name,n,steps,max_steps", [("default", 4096, 250, 100), ("twin", 2048, 250, 60),
+                                                    ("mirror", 1024, 150, 0)])
+def test_cuda_matches_c_oracle_philox(VTG, name, n, steps, max_steps):
+    """BASELINE config 2 shape: batched envs, uniform-random actions, time-limit auto-reset."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import gen_golden
+    lvt = gen_golden.variant_levels()[name]
+    seed = 0xC0FFEE + n
+    env = VTG(n, seed=seed, max_episode_steps=max_steps, auto_reset=True, levels=[product_level(lvt)], render=False)
+    cb = c_oracle.CBatch(c_oracle.CLevel(lvt), n, first_env_id=0, seed=seed, max_episode_steps=max_steps, auto_reset=True)
+    cb.reset()
+    assert_state_equal(env, cb, "after construction")
+    g = torch.Generator().manual_seed(n)
+    for t in range(steps):
+        if t % 3 == 2:       # runnable actions two steps out of three keep the episodes moving
+            a = torch.randint(0, 9, (n,), generator=g, dtype=torch.int32)
+        else:
+            m = torch.from_numpy(cb.mask().astype(np.float32)) + 1e-6
+            a = torch.multinomial(m, 1, generator=g).squeeze(1).to(torch.int32)
+        out = env.step_raw(a.cuda())
+        ref = cb.step(a.numpy())
+        assert_step_equal(out, ref, "step %d" % t)
+        if t % 25 == 24:
+            assert_state_equal(env, cb, "step %d" % t)
+            np.testing.assert_array_equal(env.available_mask.cpu().numpy(), cb.mask())
+    assert_state_equal(env, cb, "final")
+    st = env.stats()
+    assert list(st.values()) == cb.stats().tolist()
+    assert st["errors"] == 0 and st["gym_steps"] == n * steps
+    env.close()
+
+
+def test_mixed_level_batch(VTG):
+    """BASELINE config 5: one batch mixing several layouts."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import gen_golden
+    lv = gen_golden.variant_levels()
+    names = ["default", "mirror", "twin", "altinit"]
+    n, seed = 1536, 99
+    rng = np.random.default_rng(5)
+    ids = rng.integers(0, len(names), n).astype(np.uint8)
+    env = VTG(n, seed=seed, max_episode_steps=50, auto_reset=True, levels=[product_level(lv[k]) for k in names],
+              level_ids=ids, render=False)
+    refs = [c_oracle.CBatch(c_oracle.CLevel(lv[k]), n, first_env_id=0, seed=seed, max_episode_steps=50, auto_reset=True)
+            for k in names]
+    for r in refs:
+        r.reset()
+    g = torch.Generator().manual_seed(1)
+    for t in range(120):
+        a = torch.randint(0, 9, (n,), generator=g, dtype=torch.int32)
+        if t % 2:
+            masks = np.stack([r.mask() for r in refs])[ids, np.arange(n)]
+            a = torch.multinomial(torch.from_numpy(masks.astype(np.float32)) + 1e-6, 1, generator=g).squeeze(1).to(torch.int32)
+        obs, rew, done, ran = env.step_raw(a.cuda())
+        outs = [r.step(a.numpy()) for r in refs]
+        for l in range(len(names)):
+            sel = ids == l
+            o2, r2, d2, ran2, _ = outs[l]
+            np.testing.assert_array_equal(rew.cpu().numpy()[sel], r2[sel])
+            np.testing.assert_array_equal(done.cpu().numpy()[sel], d2[sel])
+            np.testing.assert_array_equal(ran.cpu().numpy()[sel], ran2[sel])
+            od = o2.shape[1]
+            np.testing.assert_array_equal(obs.cpu().numpy()[sel][:, :od], o2[sel].astype(np.float32))
+            assert not obs.cpu().numpy()[sel][:, od:].any()      # padding columns are zero
+    st = {k: v.cpu().numpy() for k, v in env.get_state().items()}
+    for l in range(len(names)):
+        sel = ids == l
+        cs = refs[l].state()
+        np.testing.assert_array_equal(st["pos"][sel], cs["pos"][sel])
+        np.testing.assert_array_equal(st["misc"][sel], cs["misc"][sel])
+        np.testing.assert_array_equal(st["angles"][sel][:, : refs[l].level.nh], cs["angles"][sel])
+    env.close()
+
+
+def test_sharding_is_invisible(VTG):
+    """N envs on one device == the same env ids split over shards, bit-exact."""
+    from gym_treasure_game_b200 import shard_range
+    n, seed = 3000, 7
+    whole = VTG(n, seed=seed, max_episode_steps=40, render=False)
+    parts = []
+    for r in range(3):
+        lo, hi = shard_range(n, r, 3)
+        parts.append((lo, hi, VTG(hi - lo, seed=seed, max_episode_steps=40, first_env_id=lo, render=False)))
+    g = torch.Generator().manual_seed(3)
+    for t in range(80):
+        a = torch.randint(0, 9, (n,), generator=g, dtype=torch.int32).cuda()
+        o, r, d, _ = whole.step_raw(a)
+        for lo, hi, p in parts:
+            o2, r2, d2, _ = p.step_raw(a[lo:hi].contiguous())
+            assert torch.equal(o[lo:hi], o2) and torch.equal(r[lo:hi], r2) and torch.equal(d[lo:hi], d2)
+    tot = sum(np.array(list(p.stats().values())) for _, _, p in parts)
+    assert tot.tolist() == list(whole.stats().values())
+
+
+def test_state_roundtrip_and_injection(VTG):
+    n = 512
+    env = VTG(n, seed=5, render=False)
+    g = torch.Generator().manual_seed(0)
+    for _ in range(30):
+        env.step_raw(torch.randint(0, 9, (n,), generator=g, dtype=torch.int32).cuda())
+    s0 = {k: v.clone() for k, v in env.get_state().items()}
+    env2 = VTG(n, seed=5, render=False)
+    env2.set_state(s0)
+    s1 = env2.get_state()
+    for k in s0:
+        assert torch.equal(s0[k], s1[k]), k
+    a = torch.randint(0, 9, (n,), generator=g, dtype=torch.int32).cuda()
+    o0, r0, d0, _ = env.step_raw(a)
+    o1, r1, d1, _ = env2.step_raw(a)
+    assert torch.equal(o0, o1) and torch.equal(r0, r1) and torch.equal(d0, d1)
+
+
+def test_host_step_matches_device_step(VTG):
+    n = 2048
+    e1, e2 = VTG(n, seed=11, max_episode_steps=30, render=False), VTG(n, seed=11, max_episode_steps=30, render=False)
+    host = e2.make_host_buffers()
+    g = torch.Generator().manual_seed(2)
+    for _ in range(40):
+        a = torch.randint(0, 9, (n,), generator=g, dtype=torch.int32)
+        o, r, d, ran = e1.step_raw(a.cuda())
+        host["actions"].copy_(a)
+        e2.step_host(host)
+        assert torch.equal(o.cpu(), host["obs"]) and torch.equal(r.cpu(), host["reward"])
+        assert torch.equal(d.cpu(), host["done"]) and torch.equal(ran.cpu(), host["ran"])
