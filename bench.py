@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""Benchmark of the Treasure Game hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU algorithm
+
+Workload (BASELINE.json configs[2], the configuration the headline metric is quoted on):
+treasure_game-v0, vector-state observations, 1,048,576 environments per GPU, uniform-random
+option ids, 100-step time limit with auto-reset.  One "step" = one TreasureGame.step for every
+env of the batch (runnable or not).  N > 1: one process per GPU (torchrun), env ids sharded
+contiguously, no data-path collective; the episode-statistics vector is all-reduced with NCCL
+on a side stream every 100 steps and once at the end ("scaling": "weak").
+
+Timing: CUDA events on the launching stream around every step kernel; between timed steps a
+512 MiB buffer is overwritten to flush the 126 MB L2 (outside the event pairs); the K steps are
+bracketed by barrier + synchronize; the per-rank sum of event times is MAX-reduced over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_ENV_STEP = 125          # SURVEY.md 8(d); this layout moves 126 (52 read + 74 written)
+ALGO_BYTES_PER_FRAME = 1258024         # 624*672*3 written + 40 state bytes read
+ENVS_PER_GPU = 1 << 20
+MAX_EPISODE_STEPS = 100
+METRIC, UNIT = "env_steps_per_s", "env-steps/s"
+WORKLOAD = ("treasure_game-v0 vector-state obs, 1,048,576 envs per GPU (BASELINE configs[2] shard), "
+            "uniform-random option ids, 100-step time limit + auto-reset")
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.2):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:       # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------- CPU baselines
+def _py_worker(args):
+    seed, seconds = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import py_oracle as po
+    t0 = time.perf_counter()
+    steps = ticks = 0
+    ep = 0
+    while time.perf_counter() - t0 < seconds:
+        s, t = po.readme_loop(seed * 100003 + ep, episodes=5)        # README loop: 5 episodes x 100 steps
+        steps += s
+        ticks += t
+        ep += 1
+    return steps, ticks, time.perf_counter() - t0
+
+
+def cpu_baseline_python(seconds, procs=None):
+    """The reference's algorithm (pure-Python port, oracle/py_oracle.py, pinned bit-exact against the
+    reference) in P independent processes -- BASELINE.md section 3."""
+    import multiprocessing as mp
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_py_worker, [(i + 1, seconds) for i in range(procs)])
+    steps = sum(r[0] for r in res)
+    ticks = sum(r[1] for r in res)
+    wall = max(r[2] for r in res)
+    return {"value": steps / wall, "unit": UNIT, "cores": procs, "kind": "port",
+            "sample": "README loop (5 episodes x 100 uniform-random steps, reset per episode) repeated for "
+                      "%.0f s in %d processes; pure-Python port of the reference (oracle/py_oracle.py)" % (seconds, procs),
+            "primitive_ticks_per_s": ticks / wall, "per_core": steps / wall / procs}
+
+
+def cpu_baseline_c(seconds, threads=None, envs_per_thread=4096):
+    """Secondary, much stronger baseline: the plain-C port (oracle/tg_oracle.c), one batch per thread."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import c_oracle
+    import py_oracle as po
+    threads = threads or os.cpu_count() or 1
+    lv = c_oracle.CLevel(po.default_level())
+    batches = [c_oracle.CBatch(lv, envs_per_thread, first_env_id=i * envs_per_thread, seed=0,
+                               max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True) for i in range(threads)]
+    for b in batches:
+        b.reset()
+    counts = [0] * threads
+
+    def work(i):
+        rng = np.random.default_rng(i)
+        rew = np.zeros(envs_per_thread, np.float32)
+        done = np.zeros(envs_per_thread, np.uint8)
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            a = rng.integers(0, 9, envs_per_thread, dtype=np.int32)
+            batches[i].step_fast(a, rew, done)          # ctypes releases the GIL
+            counts[i] += envs_per_thread
+
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    wall = time.perf_counter() - t0
+    return {"value": sum(counts) / wall, "unit": UNIT, "cores": threads, "kind": "port-c",
+            "sample": "%d envs per thread, random actions, auto-reset, %.0f s" % (envs_per_thread, seconds)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    per_step = 2.0
+    res = None
+    t_all = time.perf_counter()
+    vals = []
+    for k in range(args.warmup + args.steps):
+        r = cpu_baseline_python(per_step)
+        if k >= args.warmup:
+            vals.append(r)
+        res = r
+    wall = time.perf_counter() - t_all
+    value = sum(v["value"] for v in vals) / len(vals)
+    res["value"] = value
+    res["sample"] = ("each step = " + res["sample"])
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU arm: reference algorithm (pure-Python port; the Python "
+                       "reference itself cannot travel to the GPU box), all host cores, README loop"},
+            "cpu_baseline": res,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": wall}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary configs (4096 envs, RGB render, CPU baselines)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from gym_treasure_game_b200 import VectorTreasureGame
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs_per_gpu
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    env = VectorTreasureGame(n, device=dev, seed=0, max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True,
+                             first_env_id=rank * n, render=False)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pool = [torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device=dev) for _ in range(8)]
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    side = torch.cuda.Stream(device=dev)
+    stats_buf = torch.zeros(8, dtype=torch.int64, device=dev)
+
+    def stats_allreduce():
+        # the path's only collective: 64-byte int64[8] sum, off the critical path
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            stats_buf.copy_(env.stats_tensor())
+            if world > 1:
+                dist.all_reduce(stats_buf)
+
+    for k in range(W):
+        env.step_raw(pool[k % len(pool)])
+    env.clear_stats()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    launches0 = env.launch_count
+    t_wall0 = time.perf_counter()
+    for k in range(K):
+        flush.zero_()                                   # L2 flush, outside the event pair
+        starts[k].record()
+        env.step_raw(pool[k % len(pool)])
+        ends[k].record()
+        if (k + 1) % 100 == 0:
+            stats_allreduce()
+    stats_allreduce()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = env.launch_count - launches0
+    clocks = sampler.finish()
+    per_step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = torch.tensor([sum(per_step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) / 1000.0
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    stats = dict(zip(["episodes", "successes", "return_sum", "episode_steps_sum", "primitive_ticks",
+                      "runnable_steps", "gym_steps", "errors"], (int(v) for v in stats_buf.cpu())))
+    value = world * n * K / total_s
+
+    # ---- end-to-end through the C ABI with HOST buffers (tg_step_host): H2D actions, step, D2H results
+    Ke = min(K, 20)
+    host = env.make_host_buffers()
+    hpool = [p.cpu().pin_memory() for p in pool[:4]]
+    for k in range(3):
+        host["actions"] = hpool[k % len(hpool)]
+        env.step_host(host)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(Ke):
+        host["actions"] = hpool[k % len(hpool)]
+        env.step_host(host)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * Ke / float(e2e_s.item())
+    h2d = n * 4
+    d2h = n * (env.obs_dim * 4 + 4 + 1 + 1)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": 1000.0 * total_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32+f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "envs_per_gpu": n, "total_envs": n * world, "max_episode_steps": MAX_EPISODE_STEPS,
+                   "l2": "512 MiB buffer overwritten between timed steps (outside the event pairs)",
+                   "actions": "8 pre-generated device batches cycled", "collective": "NCCL all-reduce of int64[8] stats every 100 steps, side stream"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                "api": "tg_step_host (pinned host buffers; copies + stream sync inside the call)"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": (n * ALGO_BYTES_PER_ENV_STEP) / (total_s / K) / 1e9,
+                     "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
+                     "kernel": "tg_step_kernel<false,2>", "algorithmic_bytes_per_launch": n * ALGO_BYTES_PER_ENV_STEP},
+        "work": {"runnable_fraction": stats["runnable_steps"] / max(stats["gym_steps"], 1),
+                 "primitive_ticks_per_step": stats["primitive_ticks"] / max(stats["gym_steps"], 1),
+                 "primitive_ticks_per_s": stats["primitive_ticks"] / total_s if stats["gym_steps"] else None,
+                 "stats_all_ranks": stats},
+        "wall_s_timed_region_incl_flush": t_wall,
+    }
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = json.load(open(peaks_path))["hbm_gbs"]
+        line["roofline"]["peak_source"] = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak = 6650.0
+        line["roofline"]["peak_source"] = "B200_PROFILING.md fallback (of fallback)"
+    line["roofline"]["peak"] = peak
+    line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
+    traffic_path = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+    if os.path.exists(traffic_path):
+        line["roofline"]["traffic"] = json.load(open(traffic_path)).get("dram_bytes_per_launch")
+
+    env.close()
+    del env, pool
+    torch.cuda.empty_cache()
+
+    if rank == 0 and world == 1 and not args.no_aux:
+        line["aux"] = aux_configs(torch, dev, peak)
+        line["cpu_baseline"] = cpu_baseline_python(args.cpu_seconds)
+        line["cpu_baseline_c"] = cpu_baseline_c(min(args.cpu_seconds, 6.0))
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def aux_configs(torch, dev, peak):
+    """BASELINE configs[1] (4096 envs) and configs[3] (16384 envs, RGB render) on one GPU."""
+    from gym_treasure_game_b200 import VectorTreasureGame
+    out = {}
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev).manual_seed(7)
+
+    def timed(fn, iters, warm=5):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(iters):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record()
+            e.synchronize()
+            tot += s.elapsed_time(e)
+        return tot / iters / 1000.0
+
+    # configs[1]: 4096 envs
+    n = 4096
+    env = VectorTreasureGame(n, device=dev, seed=0, max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True, render=False)
+    pool = [torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device=dev) for _ in range(16)]
+    it = [0]
+
+    def step4096():
+        env.step_raw(pool[it[0] % 16]); it[0] += 1
+    for _ in range(100):
+        step4096()
+    t = timed(step4096, 300)
+    out["cfg2_4096_envs"] = {"env_steps_per_s": n / t, "ms_per_step": t * 1e3,
+                             "roofline_frac": n * ALGO_BYTES_PER_ENV_STEP / t / 1e9 / peak}
+    env.close()
+
+    # configs[3]: 16384 envs, RGB observations
+    n = 16384
+    env = VectorTreasureGame(n, device=dev, seed=0, max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True, render=True)
+    pool = [torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device=dev) for _ in range(8)]
+    frames = torch.empty((n, 624, 672, 3), dtype=torch.uint8, device=dev)
+    for k in range(20):
+        env.step_raw(pool[k % 8])
+    t_r = timed(lambda: env.render(out=frames), 10, warm=3)
+
+    def step_render():
+        env.step_raw(pool[it[0] % 8]); it[0] += 1
+        env.render(out=frames)
+    t_sr = timed(step_render, 10, warm=3)
+    out["cfg4_render_16384_envs"] = {
+        "frames_per_s_render_only": n / t_r, "frames_per_s_step_plus_render": n / t_sr, "ms_render": t_r * 1e3,
+        "roofline": {"bound": "hbm", "achieved": n * ALGO_BYTES_PER_FRAME / t_r / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": n * ALGO_BYTES_PER_FRAME / t_r / 1e9 / peak, "kernel": "tg_render_kernel",
+                     "note": "20.6 GB written per launch (> L2)"}}
+    env.close()
+    return out
+
+
+if __name__ == "__main__":
+    main()
