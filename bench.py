@@ -100,20 +100,26 @@ def _py_worker(args):
     return steps, ticks, time.perf_counter() - t0
 
 
-def cpu_baseline_python(seconds, procs=None):
+def cpu_baseline_python(seconds, procs=None, pool=None):
     """The reference's algorithm (pure-Python port, oracle/py_oracle.py, pinned bit-exact against the
     reference) in P independent processes -- BASELINE.md section 3."""
     import multiprocessing as mp
     procs = procs or os.cpu_count() or 1
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(procs) as pool:
+    own = pool is None
+    if own:
+        pool = mp.get_context("spawn").Pool(procs)
+    try:
         res = pool.map(_py_worker, [(i + 1, seconds) for i in range(procs)])
+    finally:
+        if own:
+            pool.close()
+            pool.join()
     steps = sum(r[0] for r in res)
     ticks = sum(r[1] for r in res)
     wall = max(r[2] for r in res)
     return {"value": steps / wall, "unit": UNIT, "cores": procs, "kind": "port",
             "sample": "README loop (5 episodes x 100 uniform-random steps, reset per episode) repeated for "
-                      "%.0f s in %d processes; pure-Python port of the reference (oracle/py_oracle.py)" % (seconds, procs),
+                      "%.2f s in %d processes; pure-Python port of the reference (oracle/py_oracle.py)" % (seconds, procs),
             "primitive_ticks_per_s": ticks / wall, "per_core": steps / wall / procs}
 
 
@@ -154,21 +160,32 @@ def cpu_baseline_c(seconds, threads=None, envs_per_thread=4096):
 
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args, rank):
+    """CPU arm: every "step" is a bounded sample (README loops for `per_step` seconds on all host
+    cores); the whole run is sized to about two minutes whatever K and W are."""
     if rank != 0:
         return
-    per_step = 2.0
-    res = None
+    import multiprocessing as mp
+    procs = os.cpu_count() or 1
+    total = args.warmup + args.steps
+    per_step = max(0.25, min(2.0, 120.0 / total))
+    pool = mp.get_context("spawn").Pool(procs)
     t_all = time.perf_counter()
     vals = []
-    for k in range(args.warmup + args.steps):
-        r = cpu_baseline_python(per_step)
-        if k >= args.warmup:
-            vals.append(r)
-        res = r
+    try:
+        for k in range(total):
+            r = cpu_baseline_python(per_step, procs, pool)
+            if k >= args.warmup:
+                vals.append(r)
+    finally:
+        pool.close()
+        pool.join()
     wall = time.perf_counter() - t_all
     value = sum(v["value"] for v in vals) / len(vals)
+    res = dict(vals[-1])
     res["value"] = value
-    res["sample"] = ("each step = " + res["sample"])
+    res["primitive_ticks_per_s"] = sum(v["primitive_ticks_per_s"] for v in vals) / len(vals)
+    res["per_core"] = value / procs
+    res["sample"] = "each step = " + res["sample"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
@@ -221,7 +238,12 @@ def main():
     env = VectorTreasureGame(n, device=dev, seed=0, max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True,
                              first_env_id=rank * n, render=False)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    pool = [torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device=dev) for _ in range(8)]
+    actions = torch.empty((n,), dtype=torch.int32, device=dev)
+
+    def new_actions():
+        # i.i.d. uniform option ids, regenerated on the device for every step (BASELINE configs[1]/[2]);
+        # a short cycled pool would make every env's action sequence periodic and shrink the work
+        return torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device=dev, out=actions)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     side = torch.cuda.Stream(device=dev)
     stats_buf = torch.zeros(8, dtype=torch.int64, device=dev)
@@ -235,7 +257,7 @@ def main():
                 dist.all_reduce(stats_buf)
 
     for k in range(W):
-        env.step_raw(pool[k % len(pool)])
+        env.step_raw(new_actions())
     env.clear_stats()
     barrier()
     sampler = ClockSampler(local)
@@ -245,9 +267,10 @@ def main():
     launches0 = env.launch_count
     t_wall0 = time.perf_counter()
     for k in range(K):
+        new_actions()                                   # not timed: inputs are resident before the event pair
         flush.zero_()                                   # L2 flush, outside the event pair
         starts[k].record()
-        env.step_raw(pool[k % len(pool)])
+        env.step_raw(actions)
         ends[k].record()
         if (k + 1) % 100 == 0:
             stats_allreduce()
@@ -270,7 +293,7 @@ def main():
     # ---- end-to-end through the C ABI with HOST buffers (tg_step_host): H2D actions, step, D2H results
     Ke = min(K, 20)
     host = env.make_host_buffers()
-    hpool = [p.cpu().pin_memory() for p in pool[:4]]
+    hpool = [new_actions().cpu().pin_memory() for _ in range(Ke)]
     for k in range(3):
         host["actions"] = hpool[k % len(hpool)]
         env.step_host(host)
@@ -293,7 +316,7 @@ def main():
         "dtype": "int32+f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs_per_gpu": n, "total_envs": n * world, "max_episode_steps": MAX_EPISODE_STEPS,
                    "l2": "512 MiB buffer overwritten between timed steps (outside the event pairs)",
-                   "actions": "8 pre-generated device batches cycled", "collective": "NCCL all-reduce of int64[8] stats every 100 steps, side stream"},
+                   "actions": "torch.randint on the device before every step, outside the timed event pair", "collective": "NCCL all-reduce of int64[8] stats every 100 steps, side stream"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "api": "tg_step_host (pinned host buffers; copies + stream sync inside the call)"},
@@ -321,7 +344,7 @@ def main():
         line["roofline"]["traffic"] = json.load(open(traffic_path)).get("dram_bytes_per_launch")
 
     env.close()
-    del env, pool
+    del env
     torch.cuda.empty_cache()
 
     if rank == 0 and world == 1 and not args.no_aux:
@@ -358,11 +381,11 @@ def aux_configs(torch, dev, peak):
     # configs[1]: 4096 envs
     n = 4096
     env = VectorTreasureGame(n, device=dev, seed=0, max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True, render=False)
-    pool = [torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device=dev) for _ in range(16)]
+    pool = [torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device=dev) for _ in range(512)]
     it = [0]
 
     def step4096():
-        env.step_raw(pool[it[0] % 16]); it[0] += 1
+        env.step_raw(pool[it[0] % 512]); it[0] += 1        # 512 distinct i.i.d. batches: no periodicity within a run
     for _ in range(100):
         step4096()
     t = timed(step4096, 300)
@@ -373,14 +396,14 @@ def aux_configs(torch, dev, peak):
     # configs[3]: 16384 envs, RGB observations
     n = 16384
     env = VectorTreasureGame(n, device=dev, seed=0, max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True, render=True)
-    pool = [torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device=dev) for _ in range(8)]
+    pool = [torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device=dev) for _ in range(64)]
     frames = torch.empty((n, 624, 672, 3), dtype=torch.uint8, device=dev)
-    for k in range(20):
-        env.step_raw(pool[k % 8])
+    for k in range(40):
+        env.step_raw(pool[k % 64])
     t_r = timed(lambda: env.render(out=frames), 10, warm=3)
 
     def step_render():
-        env.step_raw(pool[it[0] % 8]); it[0] += 1
+        env.step_raw(pool[it[0] % 64]); it[0] += 1
         env.render(out=frames)
     t_sr = timed(step_render, 10, warm=3)
     out["cfg4_render_16384_envs"] = {

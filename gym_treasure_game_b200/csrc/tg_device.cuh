@@ -57,18 +57,22 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 
+// One uniform draw as the 53-bit integer k with u = k / 2^53 (exactly CPython's random()).
 template <bool TAPE, int NI>
-__device__ __forceinline__ double draw(Env<NI> &e) {
+__device__ __forceinline__ uint64_t draw_k(Env<NI> &e) {
     uint32_t d = e.draws++;
-    if (TAPE) return e.tape[d];
+    if (TAPE) return (uint64_t)__double2ull_rz(e.tape[d] * 9007199254740992.0);   // exact: MT outputs are multiples of 2^-53
     uint32_t b = d >> 1;
     if (b != e.blk) {
         philox4x32_10(b, 0u, e.id_lo, e.id_hi, e.key0, e.key1, e.w0, e.w1, e.w2, e.w3);
         e.blk = b;
     }
     uint32_t a = (d & 1u) ? e.w2 : e.w0, c = (d & 1u) ? e.w3 : e.w1;
-    return ((double)(a >> 5) * 67108864.0 + (double)(c >> 6)) * (1.0 / 9007199254740992.0);
+    return ((uint64_t)(a >> 5) << 26) | (uint64_t)(c >> 6);
 }
+__device__ __forceinline__ double k_to_unit(uint64_t k) { return (double)k * (1.0 / 9007199254740992.0); }   // exact
+template <bool TAPE, int NI>
+__device__ __forceinline__ double draw(Env<NI> &e) { return k_to_unit(draw_k<TAPE>(e)); }
 
 // CPython random.uniform(a, b) = a + (b - a) * random(): two separately rounded operations.
 __device__ __forceinline__ double uniform_span(double lo, double span, double u) {
@@ -83,10 +87,9 @@ __device__ __forceinline__ double handle_angle(bool up, double u) {
 // ---------------------------------------------------------------------------
 // tiles
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int pad_cell(int v) {       // pixel -> padded cell index (floor(v/48)+PAD)
-    int t = max(v + PAD * S, 0);
-    return min((int)((unsigned)t / (unsigned)S), TSTRIDE - 1);
-}
+// pixel -> padded cell index floor(v/48)+PAD.  No clamps: px in [0, W) and py in [-S, H) are invariants of
+// the dynamics (tg_set_state clamps injected positions), so every probe lands inside the 32x32 table.
+__device__ __forceinline__ int pad_cell(int v) { return (int)((unsigned)(v + PAD * S) / (unsigned)S); }
 __device__ __forceinline__ int pad_idx(int c) { return min(max(c + PAD, 0), TSTRIDE - 1); }
 
 // effective type of the cell with padded indices (ixp, iyp)    impl:218-225 + objs:246-253
@@ -161,7 +164,7 @@ __device__ __forceinline__ bool obj_value(const LevelBlob &L, uint32_t f, int o)
 // set_val of door / handle / bolt (objs:145-149, :175-178, :231-235); returns true when the value
 // changed (the caller then runs process_trigger).  A handle redraws its angle (objs:127-131).
 template <bool TAPE, int NI>
-__device__ bool apply_val(Env<NI> &e, const LevelBlob &L, int o, bool v) {
+__device__ __forceinline__ bool apply_val(Env<NI> &e, const LevelBlob &L, int o, bool v) {
     int k = L.obj_kind[o], i = L.obj_idx[o];
     int bit = (k == TG_DOOR) ? F_DOORS + i : (k == TG_HANDLE) ? F_HANDLES + i : F_BOLTS + i;
     if ((bool)((e.flags >> bit) & 1u) == v) return false;
@@ -173,7 +176,7 @@ __device__ bool apply_val(Env<NI> &e, const LevelBlob &L, int o, bool v) {
 // set_val + recursive process_trigger (objs:76-94) as an explicit DFS.  `pt` is the set of
 // objects whose previously_triggered flag is raised (those on the DFS stack).
 template <bool TAPE, int NI>
-__device__ void set_val(Env<NI> &e, const LevelBlob &L, int o0, bool v0) {
+__device__ __forceinline__ void set_val(Env<NI> &e, const LevelBlob &L, int o0, bool v0) {
     if (!apply_val<TAPE>(e, L, o0, v0)) return;
     uint8_t st_src[TG_MAX_OBJECTS], st_t[TG_MAX_OBJECTS];
     int sp = 0;
@@ -201,7 +204,7 @@ __device__ void set_val(Env<NI> &e, const LevelBlob &L, int o0, bool v0) {
 
 // impl:434-439: the first key in bag order leaves the bag and goes to cell (-1,-1)
 template <int NI>
-__device__ void drop_key(Env<NI> &e, const LevelBlob &L) {
+__device__ __forceinline__ void drop_key(Env<NI> &e, const LevelBlob &L) {
     int len = bag_len(e.flags);
     uint32_t ord = e.flags >> F_BAGORD;
     for (int j = 0; j < len; j++) {
@@ -221,13 +224,13 @@ __device__ void drop_key(Env<NI> &e, const LevelBlob &L) {
 
 // impl:321-329
 template <bool TAPE, int NI>
-__device__ __noinline__ void interact(Env<NI> &e, const LevelBlob &L) {
+__device__ __forceinline__ void interact(Env<NI> &e, const LevelBlob &L) {
     for (int o = 0; o < L.n_objs; o++) {
         int k = L.obj_kind[o], i = L.obj_idx[o];
         if (k == TG_HANDLE) {
             if (!near_px(e.px, e.py, L.handle_cx[i] * S, L.handle_cy[i] * S, 36 * 36)) continue;   // objs:115
             bool up = (e.flags >> (F_HANDLES + i)) & 1u;
-            if (uniform_span(0.0, 1.0, draw<TAPE>(e)) <= 0.8) set_val<TAPE>(e, L, o, !up);       // objs:117-122
+            if (draw_k<TAPE>(e) <= 7205759403792794ull) set_val<TAPE>(e, L, o, !up);   // objs:117-122: uniform(0,1) <= 0.8  (0.8 * 2^53)
             else e.angles[(int64_t)i * e.n] = handle_angle(up, draw<TAPE>(e));
         } else if (k == TG_BOLT) {
             if (!near_px(e.px, e.py, L.bolt_cx[i] * S, L.bolt_cy[i] * S, 24 * 24)) continue;
@@ -239,12 +242,18 @@ __device__ __noinline__ void interact(Env<NI> &e, const LevelBlob &L) {
 // ---------------------------------------------------------------------------
 // primitive tick  (impl:290-359)
 // ---------------------------------------------------------------------------
-// impl:361-366: int(round(uniform(-4,-2))) or int(round(uniform(2,4))), round-half-even
-template <bool TAPE, int NI>
-__device__ __forceinline__ int noisy(Env<NI> &e, bool negative) {
-    double u = draw<TAPE>(e);
-    return __double2int_rn(uniform_span(negative ? -4.0 : 2.0, 2.0, u));
+// impl:361-366: int(round(uniform(-4,-2))) or int(round(uniform(2,4))) with Python's round-half-even,
+// evaluated exactly in integers.  With u = k/2^53: fl(c + 2u) = c + m*2^-51 where m = k/2 rounded to
+// nearest-even (the binade [2,4) has ulp 2^-51), and rint(c + t) = c + rint(t) for the even integers
+// c = -4, 2; rint(m/2^51) is 0 up to and including the tie m = 2^50, 2 from the tie m = 3*2^50 on.
+// (Checked against CPython on 2e6 random and all threshold-adjacent k: tests/test_rng_integer_forms.py.)
+__device__ __forceinline__ int noisy_from_k(uint64_t k, bool negative) {
+    const uint64_t q = k >> 1, m = q + (k & q & 1ull);
+    const int r = (int)(m > (1ull << 50)) + (int)(m >= (3ull << 50));
+    return (negative ? -4 : 2) + r;
 }
+template <bool TAPE, int NI>
+__device__ __forceinline__ int noisy(Env<NI> &e, bool negative) { return noisy_from_k(draw_k<TAPE>(e), negative); }
 
 template <bool TAPE, int NI>
 __device__ __forceinline__ void tick(Env<NI> &e, const LevelBlob &L, int act) {
@@ -260,7 +269,7 @@ __device__ __forceinline__ void tick(Env<NI> &e, const LevelBlob &L, int act) {
         if (side_free(L, e.flags, e.px + 16, e.py)) { xd = noisy<TAPE>(e, false); e.flags |= 1u << F_FACING; }
     } else if (act == A_JUMP) {
         if (!can_go_down(L, e.flags, e.px, e.py) && up_clear(L, e.flags, e.px, e.py))
-            e.flags = set_ticker(e.flags, draw<TAPE>(e) > 0.25 ? 23 : 22);            // impl:316-319
+            e.flags = set_ticker(e.flags, draw_k<TAPE>(e) > (1ull << 51) ? 23 : 22);   // impl:316-319: random() > 0.25
     } else if (act == A_INTERACT) {
         interact<TAPE>(e, L);
     }
@@ -322,7 +331,7 @@ __device__ __forceinline__ bool closed_door_at(const LevelBlob &L, uint32_t flag
 
 // go_left (s=-1) / go_right (s=+1): can_run + target column.  opts:23-67 / opts:95-139
 template <int NI>
-__device__ bool walk_setup(const Env<NI> &e, const LevelBlob &L, int s, int &tcx) {
+__device__ __forceinline__ bool walk_setup(const Env<NI> &e, const LevelBlob &L, int s, int &tcx) {
     int pcx, pcy; player_cell(e, pcx, pcy);
     const uint32_t f = e.flags;
     bool ok = type_c(L, f, pcx, pcy) == T_OPEN && type_c(L, f, pcx, pcy + 1) != T_OPEN;
@@ -346,7 +355,7 @@ __device__ __forceinline__ bool landing(const LevelBlob &L, uint32_t f, int cx, 
 // Evaluates can_run of option k (tg:83-89 / opt:22) and, for the options that walk to a
 // column, the target column.  err is set when the reference would raise (target None).
 template <int NI>
-__device__ bool option_setup(const Env<NI> &e, const LevelBlob &L, int k, int &tcx, bool &err) {
+__device__ __forceinline__ bool option_setup(const Env<NI> &e, const LevelBlob &L, int k, int &tcx, bool &err) {
     const uint32_t f = e.flags;
     tcx = 0; err = false;
     int pcx, pcy;
@@ -385,15 +394,11 @@ __device__ bool option_setup(const Env<NI> &e, const LevelBlob &L, int k, int &t
     return false;      // out-of-range action: the reference raises IndexError (tg:92); we report "not run"
 }
 
-// Runs option k to termination.  Returns the number of primitive ticks (0 = not runnable,
-// reference returns None); reward = -ticks - 4*[jump option]  (impl:15-16,356-359).
+// Runs option k (already known to be runnable, target column tcx from option_setup) to
+// termination.  Returns the number of primitive ticks; reward = -ticks - 4*[jump option]
+// (impl:15-16,356-359).
 template <bool TAPE, int NI>
-__device__ int run_option(Env<NI> &e, const LevelBlob &L, int k) {
-    int tcx; bool err;
-    if (!option_setup(e, L, k, tcx, err)) {
-        if (err) e.flags |= 1u << F_ERROR;
-        return 0;
-    }
+__device__ __forceinline__ int run_option_to_end(Env<NI> &e, const LevelBlob &L, int k, int tcx) {
     const int tpx = tcx * S + S / 2;
     const int s = (k == TG_GO_LEFT || k == TG_DOWN_LEFT || k == TG_JUMP_LEFT) ? -1 : 1;
     int n = 0;
@@ -429,6 +434,46 @@ __device__ int run_option(Env<NI> &e, const LevelBlob &L, int k) {
     return n;
 }
 
+// Setup + run (0 ticks = not runnable: the reference returns None, opt:22-23).
+template <bool TAPE, int NI>
+__device__ __forceinline__ int run_option(Env<NI> &e, const LevelBlob &L, int k) {
+    int tcx; bool err;
+    if (!option_setup(e, L, k, tcx, err)) {
+        if (err) e.flags |= 1u << F_ERROR;
+        return 0;
+    }
+    return run_option_to_end<TAPE>(e, L, k, tcx);
+}
+
+// Rough number of primitive ticks option k will take from this state (only used to group
+// environments of similar length into the same warp; any value is correct).
+template <int NI>
+__device__ __forceinline__ int estimate_ticks(const Env<NI> &e, const LevelBlob &L, int k, int tcx) {
+    const uint32_t f = e.flags;
+    const int walk = (abs(tcx * S + S / 2 - e.px) + 2) / 3;          // noisy() moves 3 px per tick on average
+    int pcx, pcy; player_cell(e, pcx, pcy);
+    switch (k) {
+    case TG_GO_LEFT: case TG_GO_RIGHT: return walk + 1;
+    case TG_UP_LADDER: {
+        int yc = pcy, n = 0;
+        while (n < TSTRIDE && (type_c(L, f, pcx, yc) == T_LADDER || type_c(L, f, pcx, yc - 1) == T_LADDER)) { yc--; n++; }
+        return max(2, (e.py - (yc + 1) * S + S) / 3);
+    }
+    case TG_DOWN_LADDER: {
+        int yc = pcy + 1, n = 0;
+        while (n < TSTRIDE && type_c(L, f, pcx, yc) == T_LADDER) { yc++; n++; }
+        return max(2, (yc * S - e.py - S) / 3 + 2);
+    }
+    case TG_INTERACT: return 1;
+    case TG_DOWN_LEFT: case TG_DOWN_RIGHT: {
+        int yc = pcy + 1, n = 0;
+        while (n < TSTRIDE && type_c(L, f, tcx, yc) == T_OPEN) { yc++; n++; }
+        return walk + 12 * n + 2;
+    }
+    default: return 24 + walk;                                       // jump: 22-23 ticks of lift + drift
+    }
+}
+
 template <int NI>
 __device__ __forceinline__ uint32_t available_bits(const Env<NI> &e, const LevelBlob &L) {   // tg:83-89
     uint32_t m = 0;
@@ -443,7 +488,7 @@ __device__ __forceinline__ uint32_t available_bits(const Env<NI> &e, const Level
 // reset  (impl:55-73, impl:168-178, objs:106-115) -- draws: one per handle (file order), then a gauss pair
 // ---------------------------------------------------------------------------
 template <bool TAPE, int NI>
-__device__ void reset_env(Env<NI> &e, const LevelBlob &L) {
+__device__ __forceinline__ void reset_env(Env<NI> &e, const LevelBlob &L) {
     e.flags = L.init_flags | (e.flags & (1u << F_ERROR));      // the error flag is sticky until tg_reset
     for (int h = 0; h < L.n_handles; h++) {
         bool up = (L.init_flags >> (F_HANDLES + h)) & 1u;
@@ -498,6 +543,20 @@ __device__ __forceinline__ bool is_done(const Env<NI> &e, const LevelBlob &L) { 
 __device__ __forceinline__ uint32_t pack_xy(int x, int y) { return ((uint32_t)x & 0xFFFFu) | ((uint32_t)y << 16); }
 __device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xFFFFu); }
 __device__ __forceinline__ int hi16(uint32_t v) { return (int)(int16_t)(v >> 16); }
+
+// position / flags / items only (enough for can_run and the option targets)
+template <int NI>
+__device__ __forceinline__ void load_core(Env<NI> &e, const BatchView &B, int64_t i) {
+    uint4 c = B.core[i];
+    e.px = lo16(c.x); e.py = hi16(c.x); e.flags = c.y;
+    e.ix[0] = lo16(c.z); e.iy[0] = hi16(c.z);
+    if (NI > 1) { e.ix[1] = lo16(c.w); e.iy[1] = hi16(c.w); }
+    if (NI > 2) {
+        uint2 h = B.items23[i];
+        e.ix[2] = lo16(h.x); e.iy[2] = hi16(h.x);
+        if (NI > 3) { e.ix[3] = lo16(h.y); e.iy[3] = hi16(h.y); }
+    }
+}
 
 template <int NI>
 __device__ __forceinline__ void load_env(Env<NI> &e, const BatchView &B, int64_t i, uint4 &acct) {
