@@ -11,6 +11,7 @@
 // so every frame byte is written to HBM exactly once with full-line bulk writes and nothing is
 // read from HBM but 48 bytes of env state (background and sprites are served from L2).
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include "tg_device.cuh"
 #include "tg_launch.h"
 
@@ -107,7 +108,7 @@ __device__ void fill_circle(const Band &b, int x, int y, int rad, uint8_t r, uin
 }
 
 __global__ void __launch_bounds__(RENDER_THREADS)
-tg_render_kernel(BatchView B, RenderView R, int64_t first, uint8_t *__restrict__ frames) {
+tg_render_band_kernel(BatchView B, RenderView R, int64_t first, uint8_t *__restrict__ frames) {
     extern __shared__ __align__(128) uint8_t band_px[];
     __shared__ uint64_t bar;
     const int bandi = blockIdx.x;
@@ -194,25 +195,329 @@ tg_render_kernel(BatchView B, RenderView R, int64_t first, uint8_t *__restrict__
     }
 }
 
+
+// ===========================================================================
+// v2: streaming renderer (single-level batches).  Persistent CTAs; a job is (unit type t, block of
+// RS_EB environments) where a unit is UR consecutive frame rows.  For the whole job the pristine
+// background rows of type t stay in shared memory (P, one TMA bulk load per job); units without
+// dynamic content are TMA-stored to the frame straight from P, units with sprites are composed
+// in one of two working copies (W0/W1: P -> W copy, per-pixel patches, TMA store).  Nothing is read
+// from L2/HBM per unit but 16-40 bytes of env state, every frame byte is written exactly once by a
+// bulk store, and several stores are in flight per SM.
+// Patches need no barriers: a thread owns the screen columns x = tid (mod RS_THREADS), so all
+// objects touching a pixel are applied by the same thread in file order; the lever (pygame
+// draw.line width 5 + filled circle) is evaluated per pixel in closed form.
+// ===========================================================================
+constexpr int RS_THREADS = 256;
+constexpr int RS_EB = 64;
+
+__device__ __forceinline__ void wait_bulk_read(int pending) {
+    switch (pending) {
+    case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.bulk.wait_group.read 5;" ::: "memory"); break;
+    default: asm volatile("cp.async.bulk.wait_group.read 6;" ::: "memory"); break;
+    }
+}
+
+struct Unit {
+    uint8_t *buf;     // UR rows x W x 3 in shared memory
+    int W, y0, UR;
+};
+
+__device__ __forceinline__ void put_px(const Unit &u, int x, int y, int r, int g, int b) {
+    uint8_t *d = u.buf + ((y - u.y0) * u.W + x) * 3;
+    d[0] = (uint8_t)r; d[1] = (uint8_t)g; d[2] = (uint8_t)b;
+}
+
+// the column of a 48-wide sprite at ox that this thread owns (or -1)
+__device__ __forceinline__ int owned_col(int ox) {
+    int sx = ((int)threadIdx.x - ox) % RS_THREADS;
+    if (sx < 0) sx += RS_THREADS;
+    return sx < S ? sx : -1;
+}
+
+__device__ __forceinline__ void blit_cols(const Unit &u, const uint32_t *__restrict__ spr, int ox, int oy) {
+    const int r0 = max(u.y0 - oy, 0), r1 = min(u.y0 + u.UR - oy, S);
+    if (r0 >= r1) return;
+    const int sx = owned_col(ox);
+    if (sx < 0) return;
+    const int x = ox + sx;
+    if (x < 0 || x >= u.W) return;
+    for (int rb = r0; rb < r1; rb += 8) {            // 8 independent loads in flight, then 8 blends
+        uint32_t px8[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) px8[q] = (rb + q < r1) ? __ldg(spr + (rb + q) * S + sx) : 0u;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const uint32_t s = px8[q];
+            const int a = s >> 24;
+            if (a == 0) continue;                    // also skips the rows beyond r1
+            uint8_t *d = u.buf + ((oy + rb + q - u.y0) * u.W + x) * 3;
+            const int sr = s & 255, sg = (s >> 8) & 255, sb = (s >> 16) & 255;
+            if (a == 255) { d[0] = (uint8_t)sr; d[1] = (uint8_t)sg; d[2] = (uint8_t)sb; }
+            else {
+                const int dr = d[0], dg = d[1], db = d[2];
+                d[0] = (uint8_t)(dr + (((sr - dr) * a) >> 8));
+                d[1] = (uint8_t)(dg + (((sg - dg) * a) >> 8));
+                d[2] = (uint8_t)(db + (((sb - db) * a) >> 8));
+            }
+        }
+    }
+}
+
+// Lever of one handle (drawer.py:258-265): pygame draw.line width 5 in (47,79,79), then a filled circle
+// of radius 4 in (255,0,0) at the end point.  One thread per plotted pixel: thread q < 5*dmax plots pixel
+// i = q % dmax of copy k = q / dmax - 2 of drawline() (x-major: (ax + sx*i, ay + sy*floor(i*dyp/dxp)),
+// y-major: roles swapped; clip_and_draw_line_width() shifts the copies along x when |dx| <= |dy|, else
+// along y); the last 64 threads plot the disc spans.  Line pixels under the disc are skipped, so the two
+// groups never write the same pixel and no barrier is needed between them.  The caller brackets this
+// with __syncthreads() because pixel ownership differs from the column-owned sprite blits.
+__device__ __forceinline__ void lever_pixels(const Unit &u, int x1, int y1, int ex, int ey, int rad,
+                                             const int8_t *disc_lo, const int8_t *disc_hi) {
+    const int q = threadIdx.x;
+    auto inside = [&](int x, int y) { return x >= 0 && x < u.W && y >= u.y0 && y < u.y0 + u.UR; };
+    auto in_disc = [&](int x, int y) {
+        const int row = y - ey + rad;
+        return row >= 0 && row < 2 * rad && x - ex >= disc_lo[row] && x - ex <= disc_hi[row];
+    };
+    int dx = ex - x1, dy = ey - y1;
+    const int sx = dx < 0 ? -1 : 1, sy = dy < 0 ? -1 : 1;
+    const bool shift_y = abs(dx) > abs(dy);
+    const int dxp = sx * dx + 1, dyp = sy * dy + 1;
+    const int dmax = max(dxp, dyp);
+    if (q < 5 * dmax && q < RS_THREADS - 64) {
+        const int k = q / dmax - 2, i = q % dmax;
+        const int ax = x1 + (shift_y ? 0 : k), ay = y1 + (shift_y ? k : 0);
+        int x, y;
+        if (dxp >= dyp) { x = ax + sx * i; y = ay + sy * ((i * dyp) / dxp); }
+        else { y = ay + sy * i; x = ax + sx * ((i * dxp) / dyp); }
+        if (inside(x, y) && !in_disc(x, y)) put_px(u, x, y, 47, 79, 79);
+    } else if (q >= RS_THREADS - 64) {
+        const int r = (q - (RS_THREADS - 64)) >> 3, c = (q - (RS_THREADS - 64)) & 7;
+        if (r < 2 * rad) {
+            const int x = ex + disc_lo[r] + c, y = ey - rad + r;
+            if (x <= ex + disc_hi[r] && inside(x, y)) put_px(u, x, y, 255, 0, 0);
+        }
+    }
+}
+static_assert(5 * 37 <= RS_THREADS - 64, "a 36-px lever needs 5*37 line threads plus 64 disc threads");
+
+__global__ void __launch_bounds__(RS_THREADS)
+tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int64_t first, int64_t count,
+                        uint8_t *__restrict__ frames) {
+    extern __shared__ __align__(128) uint8_t rs_smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint4 s_core[RS_EB];
+    __shared__ uint2 s_items23[RS_EB];
+    __shared__ short2 s_lever[RS_EB][TG_MAX_HANDLES];
+    __shared__ int8_t disc_lo[32], disc_hi[32];
+    __shared__ short4 s_obj[TG_MAX_OBJECTS];          // draw list: x = ox, y = oy, z = kind, w = index in kind
+    __shared__ int s_nobj, s_nhandles, s_nitems;
+    const int tid = threadIdx.x;
+    const uint32_t unit_bytes = (uint32_t)(UR * W * 3);
+    uint8_t *P = rs_smem, *Wb[2] = {rs_smem + unit_bytes, rs_smem + 2 * (size_t)unit_bytes};
+    const uint32_t bar_a = smem_addr(&bar);
+    const LevelBlob &L = B.levels[0];
+    const uint32_t *spr = A.sprites;
+    const int rad = S / 10;                                       // int(xscale / 10), drawer.py:265
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_nobj = L.n_objs; s_nhandles = L.n_handles; s_nitems = L.n_items;
+        for (int o = 0; o < L.n_objs; o++) {
+            const int kind = L.obj_kind[o], i = L.obj_idx[o];
+            int cx = 0, cy = 0;
+            if (kind == TG_DOOR) { cx = L.door_cx[i]; cy = L.door_cy[i]; }
+            else if (kind == TG_BOLT) { cx = L.bolt_cx[i]; cy = L.bolt_cy[i]; }
+            else if (kind == TG_HANDLE) { cx = L.handle_cx[i]; cy = L.handle_cy[i]; }
+            s_obj[o] = make_short4((short)(cx * S), (short)(cy * S), (short)kind, (short)i);
+        }
+        // filled-circle spans of pygame 1.9.x draw_fillellipse(rx = ry = rad), recorded per row
+        for (int i = 0; i < 2 * rad; i++) { disc_lo[i] = 127; disc_hi[i] = -128; }
+        int oj = 0xFFFF, ok = 0xFFFF, ix = 0, iy = rad * 64, h, i, j, k;
+        auto span = [&](int xa, int yrel, int xb) {
+            if (xa > xb) { int t = xa; xa = xb; xb = t; }
+            const int row = yrel + rad;
+            if (row < 0 || row >= 2 * rad) return;
+            disc_lo[row] = (int8_t)min((int)disc_lo[row], xa); disc_hi[row] = (int8_t)max((int)disc_hi[row], xb);
+        };
+        do {
+            h = (ix + 8) >> 6; i = (iy + 8) >> 6; j = (h * rad) / rad; k = (i * rad) / rad;
+            if (ok != k && oj != k && k < rad) { span(-h, -k - 1, h - 1); span(-h, k, h - 1); ok = k; }
+            if (oj != j && ok != j && k != j) { span(-i, j, i - 1); span(-i, -j - 1, i - 1); oj = j; }
+            ix = ix + iy / rad; iy = iy - ix / rad;
+        } while (i > h);
+    }
+    __syncthreads();
+
+    const int ntypes = H / UR;
+    const int nblocks = (int)((count + RS_EB - 1) / RS_EB);
+    const int64_t njobs = (int64_t)ntypes * nblocks;
+    uint32_t parity = 0;
+    int G = 0, lastW[2] = {-1, -1}, nd = 0;          // bulk-group bookkeeping (meaningful on thread 0)
+
+    for (int64_t job = blockIdx.x; job < njobs; job += gridDim.x) {
+        const int t = (int)(job / nblocks), blk = (int)(job % nblocks);
+        const int64_t e0 = (int64_t)blk * RS_EB;
+        const int ne = (int)min((int64_t)RS_EB, count - e0);
+        const int y0 = t * UR;
+        if (tid == 0) {
+            wait_bulk_read(0);                       // every store that still reads P / W has drained
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(unit_bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_addr(P)), "l"(A.background + (size_t)y0 * W * 3), "r"(unit_bytes), "r"(bar_a) : "memory");
+        }
+        __syncthreads();                             // previous job's readers of s_core are done
+        if (tid < ne) {
+            const int64_t env = first + e0 + tid;
+            s_core[tid] = B.core[env];
+            s_items23[tid] = B.items23 ? B.items23[env] : make_uint2(0u, 0u);
+            for (int hnd = 0; hnd < s_nhandles; hnd++) {                          // drawer.py:258-262
+                const double ang = B.angles[(int64_t)hnd * B.n + env];
+                const double th = __dadd_rn(__dmul_rn(1.5707963267948966, ang), 0.7853981633974483);
+                const double sxd = (double)(L.handle_cx[hnd] * S + S / 2), syd = (double)(L.handle_cy[hnd] * S + S);
+                s_lever[tid][hnd] = make_short2((short)(int)__dadd_rn(sxd, __dmul_rn(36.0, cos(th))),
+                                                (short)(int)__dsub_rn(syd, __dmul_rn(36.0, sin(th))));
+            }
+        }
+        __syncthreads();
+        uint32_t okw;
+        do {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(okw) : "r"(bar_a), "r"(parity) : "memory");
+        } while (!okw);
+        parity ^= 1u;
+        auto rows_hit = [&](int oy, int above, int below) { return oy + S + below > y0 && oy - above < y0 + UR; };
+        const int nobj = s_nobj, nitems = s_nitems;
+        bool static_dirty = false;                   // doors / bolts / handles sit at fixed rows: same for the whole job
+        for (int o = 0; o < nobj; o++) {
+            const short4 ob = s_obj[o];
+            if (ob.z == TG_DOOR || ob.z == TG_BOLT) static_dirty |= rows_hit(ob.y, 0, 0);
+            else if (ob.z == TG_HANDLE) static_dirty |= rows_hit(ob.y, 0, 3);
+        }
+
+        for (int uidx = 0; uidx < ne; uidx++) {
+            const uint4 c = s_core[uidx];
+            const uint32_t f = c.y;
+            const int px = lo16(c.x), py = hi16(c.x);
+            const uint32_t items[4] = {c.z, c.w, s_items23[uidx].x, s_items23[uidx].y};
+            // does anything dynamic touch rows [y0, y0+UR)?
+            bool dirty = static_dirty || rows_hit(py, 0, 0);
+#pragma unroll
+            for (int q = 0; q < TG_MAX_ITEMS; q++) dirty |= q < nitems && lo16(items[q]) >= 0 && rows_hit(hi16(items[q]), 0, 0);
+            uint8_t *dst = frames + ((size_t)(e0 + uidx) * H + (size_t)y0) * (size_t)W * 3;
+            if (!dirty) {
+                if (tid == 0) {
+                    wait_bulk_read(6);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(P)), "r"(unit_bytes) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    G++;
+                }
+                continue;
+            }
+            const int kbuf = nd & 1;
+            nd++;
+            if (tid == 0 && lastW[kbuf] >= 0) wait_bulk_read(min(G - 1 - lastW[kbuf], 6));
+            __syncthreads();
+            {   // working copy <- pristine rows
+                const uint4 *src4 = reinterpret_cast<const uint4 *>(P);
+                uint4 *dst4 = reinterpret_cast<uint4 *>(Wb[kbuf]);
+                for (uint32_t q = tid; q < unit_bytes / 16; q += RS_THREADS) dst4[q] = src4[q];
+            }
+            __syncthreads();
+            Unit u; u.buf = Wb[kbuf]; u.W = W; u.y0 = y0; u.UR = UR;
+            for (int o = 0; o < nobj; o++) {                                           // drawer.py:154-155
+                const short4 ob = s_obj[o];
+                const int kind = ob.z, i = ob.w;
+                if (kind == TG_DOOR) {
+                    const bool closed = (f >> (F_DOORS + i)) & 1u;
+                    blit_cols(u, spr + (closed ? TG_SPR_DOOR_CLOSED : TG_SPR_DOOR_OPEN) * S * S, ob.x, ob.y);
+                } else if (kind == TG_KEY || kind == TG_GOLD) {
+                    uint32_t it = items[0];
+#pragma unroll
+                    for (int q = 1; q < TG_MAX_ITEMS; q++) if (q == i) it = items[q];
+                    if (lo16(it) >= 0)                                                 // drawer.py:240-241
+                        blit_cols(u, spr + (kind == TG_KEY ? TG_SPR_KEY : TG_SPR_GOLD) * S * S, lo16(it), hi16(it));
+                } else if (kind == TG_BOLT) {
+                    const bool locked = (f >> (F_BOLTS + i)) & 1u;
+                    blit_cols(u, spr + (locked ? TG_SPR_BOLT_LOCKED : TG_SPR_BOLT_OPEN) * S * S, ob.x, ob.y);
+                } else {
+                    if (rows_hit(ob.y, 0, 3)) {        // lever rows: oy+8 .. oy+50 (uniform branch)
+                        __syncthreads();
+                        lever_pixels(u, ob.x + S / 2, ob.y + S, s_lever[uidx][i].x, s_lever[uidx][i].y, rad, disc_lo, disc_hi);
+                        __syncthreads();
+                    }
+                    blit_cols(u, spr + TG_SPR_HANDLE_BASE * S * S, ob.x, ob.y);
+                }
+            }
+            blit_cols(u, spr + ((f & 1u) ? TG_SPR_HERO_RIGHT : TG_SPR_HERO_LEFT) * S * S, px - S / 2, py);   // drawer.py:157-161
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                wait_bulk_read(6);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(Wb[kbuf])), "r"(unit_bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                lastW[kbuf] = G;
+                G++;
+            }
+        }
+    }
+    if (tid == 0) wait_bulk_read(0);                 // shared memory must outlive the last bulk store's reads
+}
+
 static bool g_render_configured = false;
+static int g_num_sms = 0;
 
 cudaError_t render_configure() {
     if (g_render_configured) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(tg_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tg_render_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tg_render_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess) g_render_configured = true;
     return e;
+}
+
+// rows per unit of the streaming renderer: the largest divisor of 48 whose three buffers fit twice per SM
+static int pick_unit_rows(int W) {
+    static const int cand[] = {48, 24, 16, 12, 8, 6, 4};
+    for (int ur : cand) if ((size_t)3 * ur * W * 3 <= 110 * 1024) return ur;
+    return 4;
 }
 
 cudaError_t launch_render(const BatchView &B, const RenderView &R, int64_t first, int64_t count,
                           uint8_t *frames, cudaStream_t s) {
     cudaError_t e = render_configure();
     if (e != cudaSuccess) return e;
+    static int force_v1 = -1;
+    if (force_v1 < 0) { const char *v = getenv("TG_RENDER_V1"); force_v1 = (v && v[0] == '1') ? 1 : 0; }
+    if (B.n_levels == 1 && !force_v1) {
+        const int ur = pick_unit_rows(R.frame_w);
+        const size_t smem = (size_t)3 * ur * R.frame_w * 3;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tg_render_stream_kernel, RS_THREADS, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        const int64_t njobs = (int64_t)(R.frame_h / ur) * ((count + RS_EB - 1) / RS_EB);
+        const int64_t grid = njobs < (int64_t)g_num_sms * per_sm ? njobs : (int64_t)g_num_sms * per_sm;
+        tg_render_stream_kernel<<<(unsigned)grid, RS_THREADS, smem, s>>>(B, R.assets[0], R.frame_w, R.frame_h, ur, first, count, frames);
+        return cudaGetLastError();
+    }
     const size_t band_bytes = (size_t)S * R.frame_w * 3;
     // grid.y is limited to 65535: render in slabs
     for (int64_t off = 0; off < count; off += 32768) {
         const int64_t c = (count - off < 32768) ? count - off : 32768;
         dim3 grid((unsigned)R.ch, (unsigned)c);
-        tg_render_kernel<<<grid, RENDER_THREADS, band_bytes, s>>>(
+        tg_render_band_kernel<<<grid, RENDER_THREADS, band_bytes, s>>>(
             B, R, first + off, frames + (size_t)off * R.frame_h * R.frame_w * 3);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
