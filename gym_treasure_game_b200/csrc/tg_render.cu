@@ -209,7 +209,10 @@ tg_render_band_kernel(BatchView B, RenderView R, int64_t first, uint8_t *__restr
 // draw.line width 5 + filled circle) is evaluated per pixel in closed form.
 // ===========================================================================
 constexpr int RS_THREADS = 256;
+constexpr int RS_PATCH_THREADS = RS_THREADS - 32;     // warps 1..7 compose dirty units; warp 0 streams clean ones
 constexpr int RS_EB = 64;
+
+__device__ __forceinline__ void patch_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(RS_PATCH_THREADS) : "memory"); }
 
 __device__ __forceinline__ void wait_bulk_read(int pending) {
     switch (pending) {
@@ -235,8 +238,8 @@ __device__ __forceinline__ void put_px(const Unit &u, int x, int y, int r, int g
 
 // the column of a 48-wide sprite at ox that this thread owns (or -1)
 __device__ __forceinline__ int owned_col(int ox) {
-    int sx = ((int)threadIdx.x - ox) % RS_THREADS;
-    if (sx < 0) sx += RS_THREADS;
+    int sx = ((int)threadIdx.x - 32 - ox) % RS_PATCH_THREADS;      // patch threads are tid 32..255
+    if (sx < 0) sx += RS_PATCH_THREADS;
     return sx < S ? sx : -1;
 }
 
@@ -278,7 +281,6 @@ __device__ __forceinline__ void blit_cols(const Unit &u, const uint32_t *__restr
 // with __syncthreads() because pixel ownership differs from the column-owned sprite blits.
 __device__ __forceinline__ void lever_pixels(const Unit &u, int x1, int y1, int ex, int ey, int rad,
                                              const int8_t *disc_lo, const int8_t *disc_hi) {
-    const int q = threadIdx.x;
     auto inside = [&](int x, int y) { return x >= 0 && x < u.W && y >= u.y0 && y < u.y0 + u.UR; };
     auto in_disc = [&](int x, int y) {
         const int row = y - ey + rad;
@@ -289,26 +291,26 @@ __device__ __forceinline__ void lever_pixels(const Unit &u, int x1, int y1, int 
     const bool shift_y = abs(dx) > abs(dy);
     const int dxp = sx * dx + 1, dyp = sy * dy + 1;
     const int dmax = max(dxp, dyp);
-    if (q < 5 * dmax && q < RS_THREADS - 64) {
-        const int k = q / dmax - 2, i = q % dmax;
-        const int ax = x1 + (shift_y ? 0 : k), ay = y1 + (shift_y ? k : 0);
-        int x, y;
-        if (dxp >= dyp) { x = ax + sx * i; y = ay + sy * ((i * dyp) / dxp); }
-        else { y = ay + sy * i; x = ax + sx * ((i * dxp) / dyp); }
-        if (inside(x, y) && !in_disc(x, y)) put_px(u, x, y, 47, 79, 79);
-    } else if (q >= RS_THREADS - 64) {
-        const int r = (q - (RS_THREADS - 64)) >> 3, c = (q - (RS_THREADS - 64)) & 7;
-        if (r < 2 * rad) {
+    const int nline = 5 * dmax, ndisc = 2 * rad * 16;              // disc: 2*rad rows x up to 16 px
+    for (int q = (int)threadIdx.x - 32; q < nline + ndisc; q += RS_PATCH_THREADS) {
+        if (q < nline) {
+            const int k = q / dmax - 2, i = q % dmax;
+            const int ax = x1 + (shift_y ? 0 : k), ay = y1 + (shift_y ? k : 0);
+            int x, y;
+            if (dxp >= dyp) { x = ax + sx * i; y = ay + sy * ((i * dyp) / dxp); }
+            else { y = ay + sy * i; x = ax + sx * ((i * dxp) / dyp); }
+            if (inside(x, y) && !in_disc(x, y)) put_px(u, x, y, 47, 79, 79);
+        } else {
+            const int r = (q - nline) >> 4, c = (q - nline) & 15;
             const int x = ex + disc_lo[r] + c, y = ey - rad + r;
             if (x <= ex + disc_hi[r] && inside(x, y)) put_px(u, x, y, 255, 0, 0);
         }
     }
 }
-static_assert(5 * 37 <= RS_THREADS - 64, "a 36-px lever needs 5*37 line threads plus 64 disc threads");
 
 __global__ void __launch_bounds__(RS_THREADS)
 tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int64_t first, int64_t count,
-                        uint8_t *__restrict__ frames) {
+                        uint8_t *__restrict__ frames, int dbg) {
     extern __shared__ __align__(128) uint8_t rs_smem[];
     __shared__ uint64_t bar;
     __shared__ uint4 s_core[RS_EB];
@@ -317,9 +319,10 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int64
     __shared__ int8_t disc_lo[32], disc_hi[32];
     __shared__ short4 s_obj[TG_MAX_OBJECTS];          // draw list: x = ox, y = oy, z = kind, w = index in kind
     __shared__ int s_nobj, s_nhandles, s_nitems;
+    __shared__ uint8_t s_dirty[RS_EB];
     const int tid = threadIdx.x;
     const uint32_t unit_bytes = (uint32_t)(UR * W * 3);
-    uint8_t *P = rs_smem, *Wb[2] = {rs_smem + unit_bytes, rs_smem + 2 * (size_t)unit_bytes};
+    uint8_t *P = rs_smem, *W0 = rs_smem + unit_bytes, *W1 = rs_smem + 2 * (size_t)unit_bytes;
     const uint32_t bar_a = smem_addr(&bar);
     const LevelBlob &L = B.levels[0];
     const uint32_t *spr = A.sprites;
@@ -401,72 +404,91 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int64
             else if (ob.z == TG_HANDLE) static_dirty |= rows_hit(ob.y, 0, 3);
         }
 
-        for (int uidx = 0; uidx < ne; uidx++) {
-            const uint4 c = s_core[uidx];
-            const uint32_t f = c.y;
-            const int px = lo16(c.x), py = hi16(c.x);
-            const uint32_t items[4] = {c.z, c.w, s_items23[uidx].x, s_items23[uidx].y};
-            // does anything dynamic touch rows [y0, y0+UR)?
-            bool dirty = static_dirty || rows_hit(py, 0, 0);
+        // which units of the job have anything dynamic in rows [y0, y0+UR)?
+        if (tid < ne) {
+            const uint4 c = s_core[tid];
+            const uint32_t items[4] = {c.z, c.w, s_items23[tid].x, s_items23[tid].y};
+            bool dirty = static_dirty || rows_hit(hi16(c.x), 0, 0);
 #pragma unroll
             for (int q = 0; q < TG_MAX_ITEMS; q++) dirty |= q < nitems && lo16(items[q]) >= 0 && rows_hit(hi16(items[q]), 0, 0);
-            uint8_t *dst = frames + ((size_t)(e0 + uidx) * H + (size_t)y0) * (size_t)W * 3;
-            if (!dirty) {
-                if (tid == 0) {
+            s_dirty[tid] = (dirty && dbg != 1) ? 1 : 0;     // dbg: timing experiments only (TG_RENDER_DBG)
+        }
+        __syncthreads();
+        uint8_t *job_dst = frames + ((size_t)e0 * H + (size_t)y0) * (size_t)W * 3;
+        const size_t frame_bytes = (size_t)H * W * 3;
+
+        if (tid < 32) {
+            // ---- role 1 (warp 0): stream the clean units straight from the pristine rows ----
+            if (tid == 0) {
+                for (int uidx = 0; uidx < ne; uidx++) {
+                    if (s_dirty[uidx]) continue;
                     wait_bulk_read(6);
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(P)), "r"(unit_bytes) : "memory");
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(job_dst + uidx * frame_bytes), "r"(smem_addr(P)), "r"(unit_bytes) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        } else {
+            // ---- role 2 (warps 1..7): compose the dirty units in W0/W1 and store them ----
+            const int pt = tid - 32;
+            for (int uidx = 0; uidx < ne; uidx++) {
+                if (!s_dirty[uidx]) continue;
+                const uint4 c = s_core[uidx];
+                const uint32_t f = c.y;
+                const int px = lo16(c.x), py = hi16(c.x);
+                const uint32_t items[4] = {c.z, c.w, s_items23[uidx].x, s_items23[uidx].y};
+                const int kbuf = nd & 1;
+                nd++;
+                uint8_t *wbuf = kbuf ? W1 : W0;
+                if (pt == 0 && lastW[kbuf] >= 0) wait_bulk_read(min(G - 1 - lastW[kbuf], 6));
+                patch_barrier();
+                {   // working copy <- pristine rows
+                    const uint4 *src4 = reinterpret_cast<const uint4 *>(P);
+                    uint4 *dst4 = reinterpret_cast<uint4 *>(wbuf);
+                    for (uint32_t q = pt; q < unit_bytes / 16; q += RS_PATCH_THREADS) dst4[q] = src4[q];
+                }
+                patch_barrier();
+                Unit u; u.buf = wbuf; u.W = W; u.y0 = y0; u.UR = UR;
+                for (int o = 0; o < ((dbg == 2 || dbg == 3) ? 0 : nobj); o++) {                      // drawer.py:154-155
+                    const short4 ob = s_obj[o];
+                    const int kind = ob.z, i = ob.w;
+                    if (kind == TG_DOOR) {
+                        const bool closed = (f >> (F_DOORS + i)) & 1u;
+                        blit_cols(u, spr + (closed ? TG_SPR_DOOR_CLOSED : TG_SPR_DOOR_OPEN) * S * S, ob.x, ob.y);
+                    } else if (kind == TG_KEY || kind == TG_GOLD) {
+                        uint32_t it = items[0];
+#pragma unroll
+                        for (int q = 1; q < TG_MAX_ITEMS; q++) if (q == i) it = items[q];
+                        if (lo16(it) >= 0)                                             // drawer.py:240-241
+                            blit_cols(u, spr + (kind == TG_KEY ? TG_SPR_KEY : TG_SPR_GOLD) * S * S, lo16(it), hi16(it));
+                    } else if (kind == TG_BOLT) {
+                        const bool locked = (f >> (F_BOLTS + i)) & 1u;
+                        blit_cols(u, spr + (locked ? TG_SPR_BOLT_LOCKED : TG_SPR_BOLT_OPEN) * S * S, ob.x, ob.y);
+                    } else {
+                        if (rows_hit(ob.y, 0, 3) && dbg != 4) {    // lever rows: oy+8 .. oy+50 (uniform branch)
+                            patch_barrier();
+                            lever_pixels(u, ob.x + S / 2, ob.y + S, s_lever[uidx][i].x, s_lever[uidx][i].y, rad, disc_lo, disc_hi);
+                            patch_barrier();
+                        }
+                        blit_cols(u, spr + TG_SPR_HANDLE_BASE * S * S, ob.x, ob.y);
+                    }
+                }
+                if (dbg != 2 && dbg != 5) blit_cols(u, spr + ((f & 1u) ? TG_SPR_HERO_RIGHT : TG_SPR_HERO_LEFT) * S * S, px - S / 2, py);   // drawer.py:157-161
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                patch_barrier();
+                if (pt == 0) {
+                    wait_bulk_read(6);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(job_dst + uidx * frame_bytes), "r"(smem_addr(wbuf)), "r"(unit_bytes) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    lastW[kbuf] = G;
                     G++;
                 }
-                continue;
-            }
-            const int kbuf = nd & 1;
-            nd++;
-            if (tid == 0 && lastW[kbuf] >= 0) wait_bulk_read(min(G - 1 - lastW[kbuf], 6));
-            __syncthreads();
-            {   // working copy <- pristine rows
-                const uint4 *src4 = reinterpret_cast<const uint4 *>(P);
-                uint4 *dst4 = reinterpret_cast<uint4 *>(Wb[kbuf]);
-                for (uint32_t q = tid; q < unit_bytes / 16; q += RS_THREADS) dst4[q] = src4[q];
-            }
-            __syncthreads();
-            Unit u; u.buf = Wb[kbuf]; u.W = W; u.y0 = y0; u.UR = UR;
-            for (int o = 0; o < nobj; o++) {                                           // drawer.py:154-155
-                const short4 ob = s_obj[o];
-                const int kind = ob.z, i = ob.w;
-                if (kind == TG_DOOR) {
-                    const bool closed = (f >> (F_DOORS + i)) & 1u;
-                    blit_cols(u, spr + (closed ? TG_SPR_DOOR_CLOSED : TG_SPR_DOOR_OPEN) * S * S, ob.x, ob.y);
-                } else if (kind == TG_KEY || kind == TG_GOLD) {
-                    uint32_t it = items[0];
-#pragma unroll
-                    for (int q = 1; q < TG_MAX_ITEMS; q++) if (q == i) it = items[q];
-                    if (lo16(it) >= 0)                                                 // drawer.py:240-241
-                        blit_cols(u, spr + (kind == TG_KEY ? TG_SPR_KEY : TG_SPR_GOLD) * S * S, lo16(it), hi16(it));
-                } else if (kind == TG_BOLT) {
-                    const bool locked = (f >> (F_BOLTS + i)) & 1u;
-                    blit_cols(u, spr + (locked ? TG_SPR_BOLT_LOCKED : TG_SPR_BOLT_OPEN) * S * S, ob.x, ob.y);
-                } else {
-                    if (rows_hit(ob.y, 0, 3)) {        // lever rows: oy+8 .. oy+50 (uniform branch)
-                        __syncthreads();
-                        lever_pixels(u, ob.x + S / 2, ob.y + S, s_lever[uidx][i].x, s_lever[uidx][i].y, rad, disc_lo, disc_hi);
-                        __syncthreads();
-                    }
-                    blit_cols(u, spr + TG_SPR_HANDLE_BASE * S * S, ob.x, ob.y);
-                }
-            }
-            blit_cols(u, spr + ((f & 1u) ? TG_SPR_HERO_RIGHT : TG_SPR_HERO_LEFT) * S * S, px - S / 2, py);   // drawer.py:157-161
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
-            if (tid == 0) {
-                wait_bulk_read(6);
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(Wb[kbuf])), "r"(unit_bytes) : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                lastW[kbuf] = G;
-                G++;
             }
         }
+        __syncthreads();                             // both roles are done with P before the next job reloads it
     }
+    if (tid == 32) wait_bulk_read(0);                // (the composer's issuer; the streamer's follows)
     if (tid == 0) wait_bulk_read(0);                 // shared memory must outlive the last bulk store's reads
 }
 
@@ -487,10 +509,14 @@ cudaError_t render_configure() {
     return e;
 }
 
-// rows per unit of the streaming renderer: the largest divisor of 48 whose three buffers fit twice per SM
+// rows per unit of the streaming renderer: the largest divisor of 48 whose three buffers fit four times per
+// SM (measured on B200, 16384 frames of 672x624: UR 6/8/12/16/24 -> 4.48/4.68/4.46/4.23/2.70 TB/s)
 static int pick_unit_rows(int W) {
+    static int forced = -1;
+    if (forced < 0) { const char *v = getenv("TG_RENDER_UR"); forced = v ? atoi(v) : 0; }
+    if (forced > 0 && 48 % forced == 0) return forced;
     static const int cand[] = {48, 24, 16, 12, 8, 6, 4};
-    for (int ur : cand) if ((size_t)3 * ur * W * 3 <= 110 * 1024) return ur;
+    for (int ur : cand) if ((size_t)3 * ur * W * 3 <= 54 * 1024) return ur;
     return 4;
 }
 
@@ -509,7 +535,9 @@ cudaError_t launch_render(const BatchView &B, const RenderView &R, int64_t first
         if (per_sm < 1) per_sm = 1;
         const int64_t njobs = (int64_t)(R.frame_h / ur) * ((count + RS_EB - 1) / RS_EB);
         const int64_t grid = njobs < (int64_t)g_num_sms * per_sm ? njobs : (int64_t)g_num_sms * per_sm;
-        tg_render_stream_kernel<<<(unsigned)grid, RS_THREADS, smem, s>>>(B, R.assets[0], R.frame_w, R.frame_h, ur, first, count, frames);
+        static int dbg = -1;
+        if (dbg < 0) { const char *v = getenv("TG_RENDER_DBG"); dbg = v ? atoi(v) : 0; }
+        tg_render_stream_kernel<<<(unsigned)grid, RS_THREADS, smem, s>>>(B, R.assets[0], R.frame_w, R.frame_h, ur, first, count, frames, dbg);
         return cudaGetLastError();
     }
     const size_t band_bytes = (size_t)S * R.frame_w * 3;
