@@ -267,9 +267,7 @@ class VectorTreasureGame:
         ``torch.distributed`` group (the only collective of this path)."""
         t = self.stats_tensor().clone()
         if all_reduce:
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized():
-                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            all_reduce_stats(t)
         return dict(zip(STAT_NAMES, (int(v) for v in t.cpu())))
 
     def clear_stats(self) -> None:
@@ -278,6 +276,15 @@ class VectorTreasureGame:
     @property
     def launch_count(self) -> int:
         return int(self._L.tg_launch_count(self._h))
+
+
+def all_reduce_stats(stats: torch.Tensor) -> torch.Tensor:
+    """Sum an int64[8] statistics vector over the ranks of the default process group, in place
+    (NCCL for CUDA tensors, gloo for CPU tensors).  No-op outside ``torch.distributed``."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    return stats
 
 
 def shard_range(total_envs: int, rank: int, world_size: int):

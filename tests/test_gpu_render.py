@@ -67,3 +67,27 @@ def test_partial_range_and_out_buffer():
     out = torch.zeros((10, 624, 672, 3), dtype=torch.uint8, device="cuda")
     part = env.render(first=20, count=10, out=out)
     assert part.data_ptr() == out.data_ptr() and torch.equal(part, full[20:30])
+
+
+def test_mixed_level_batch_frames():
+    """Two layouts in one batch go through the per-band kernel (one background per level)."""
+    from gym_treasure_game_b200 import VectorTreasureGame
+    lvts = [po.default_level(), po.mirrored_level(po.default_level())]
+    n, seed = 96, 17
+    ids = (np.arange(n) % 2).astype(np.uint8)
+    env = VectorTreasureGame(n, seed=seed, auto_reset=False, levels=[product_level(l) for l in lvts], level_ids=ids)
+    refs = [c_oracle.CBatch(c_oracle.CLevel(l), n, first_env_id=0, seed=seed) for l in lvts]
+    for r in refs:
+        r.reset()
+    bgs = [ro.background(l.tiles) for l in lvts]
+    g = torch.Generator().manual_seed(9)
+    for t in range(25):
+        masks = np.stack([r.mask() for r in refs])[ids, np.arange(n)]
+        a = torch.multinomial(torch.from_numpy(masks.astype(np.float32)) + 1e-6, 1, generator=g).squeeze(1).to(torch.int32)
+        env.step_raw(a.cuda())
+        for r in refs:
+            r.step(a.numpy())
+    frames = env.render().cpu().numpy()
+    for i in range(0, n, 7):
+        want = ro.render_frame(lvts[ids[i]], refs[ids[i]].snapshot(i), bgs[ids[i]])
+        assert np.array_equal(frames[i], want), i
