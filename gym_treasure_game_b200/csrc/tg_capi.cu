@@ -176,6 +176,28 @@ extern "C" int tg_level_create(const uint8_t *tiles, int32_t cw, int32_t ch, con
         b.trig_dst[t] = (uint8_t)(obj_of[tr.dst_kind][tr.dst_index] | (tr.dst_value ? 128 : 0));
     }
     b.n_trigs = (uint8_t)n_trigs;
+    // row bit masks (door cells read as OPEN here; closed doors are OR-ed in from door_lut at run time)
+    for (int r = 0; r < TSTRIDE; r++)
+        for (int c = 0; c < TSTRIDE; c++) {
+            const uint8_t code = b.tiles[r * TSTRIDE + c];
+            if (code & TC_HAS_DOOR) continue;
+            const int t = code & 3;
+            if (t != T_OPEN) b.row_nonopen[r] |= 1u << c;
+            if (t == T_WALL) b.row_solid[r] |= 1u << c;
+            if (t == T_LADDER) b.row_ladder[r] |= 1u << c;
+        }
+    {
+        int n_rows = 0;
+        for (int d = 0; d < b.n_doors; d++) {
+            const int r = b.door_cy[d] + PAD;
+            if (!b.row_lut[r]) b.row_lut[r] = (uint8_t)(++n_rows);          // at most TG_MAX_DOORS distinct rows
+        }
+        for (int d = 0; d < b.n_doors; d++) {
+            const int li = b.row_lut[b.door_cy[d] + PAD] - 1;
+            for (int closed = 0; closed < 64; closed++)
+                if ((closed >> d) & 1) b.door_lut[li][closed] |= 1u << (b.door_cx[d] + PAD);
+        }
+    }
     b.inv_w = 1.0f / (float)(cw * S); b.inv_h = 1.0f / (float)(ch * S);
     tg_level_info &I = lv->info;
     I.cw = cw; I.ch = ch; I.n_doors = b.n_doors; I.n_handles = b.n_handles; I.n_bolts = b.n_bolts; I.n_items = n_items;

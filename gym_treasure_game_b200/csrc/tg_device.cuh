@@ -9,6 +9,7 @@
 // /root/reference/gym_treasure_game/envs/).
 #pragma once
 #include <cuda_runtime.h>
+#include <climits>
 #include "tg_types.h"
 
 namespace tg {
@@ -27,6 +28,11 @@ struct Env {
     uint32_t blk, w0, w1, w2, w3;   // cached Philox block
     uint32_t key0, key1, id_lo, id_hi;
     const double *tape;             // parity mode: this env's slice of the draw tape
+    // row-mask cache for the two probes every tick makes (valid while playery == m_py and the doors
+    // do not move): m_fall = non-open cells of the rows of y and y+50, m_side = solid cells of the
+    // rows of y+4 and y+44; bit = padded column.  A walk never changes y, so its ticks only shift/test.
+    int m_py;
+    uint32_t m_fall, m_side;
     // where this env's handle angles live (touched only by interact / reset / obs)
     double *angles;              // angles[h * n] is handle h
     int64_t n;
@@ -141,6 +147,41 @@ __device__ __forceinline__ bool side_free(const LevelBlob &L, uint32_t flags, in
     int c = pad_cell(x);
     int t = type_p(L, flags, c, pad_cell(py + 4)) | type_p(L, flags, c, pad_cell(py + 44));
     return (t & 1) == 0;
+}
+
+// ---- row-mask forms of the per-tick probes ---------------------------------------------------
+// closed doors of padded row r as column bits (objs:246-253: a closed door cell reads DOOR, an open one OPEN)
+__device__ __forceinline__ uint32_t door_bits(const LevelBlob &L, uint32_t flags, int r) {
+    const int li = L.row_lut[r];
+    const uint32_t closed = (flags >> F_DOORS) & 63u;
+    return li ? L.door_lut[li - 1][closed] : 0u;
+}
+template <int NI>
+__device__ __forceinline__ void row_cache_fill(Env<NI> &e, const LevelBlob &L) {
+    const int r0 = pad_cell(e.py), r1 = pad_cell(e.py + 50), r2 = pad_cell(e.py + 4), r3 = pad_cell(e.py + 44);
+    e.m_fall = L.row_nonopen[r0] | door_bits(L, e.flags, r0) | L.row_nonopen[r1] | door_bits(L, e.flags, r1);
+    e.m_side = L.row_solid[r2] | door_bits(L, e.flags, r2) | L.row_solid[r3] | door_bits(L, e.flags, r3);
+    e.m_py = e.py;
+}
+// impl:283-288 through the cache
+template <int NI>
+__device__ __forceinline__ bool can_fall_m(Env<NI> &e, const LevelBlob &L) {
+    if (e.m_py != e.py) row_cache_fill(e, L);
+    return (((e.m_fall >> pad_cell(e.px - 10)) | (e.m_fall >> pad_cell(e.px + 10))) & 1u) == 0u;
+}
+// impl:259-281 through the cache (x = playerx -+ 16)
+template <int NI>
+__device__ __forceinline__ bool side_free_m(Env<NI> &e, const LevelBlob &L, int x) {
+    if (e.m_py != e.py) row_cache_fill(e, L);
+    return ((e.m_side >> pad_cell(x)) & 1u) == 0u;
+}
+// impl:240-257 in mask form: up: y > 1 and LADDER in rows of y-4, y, y+44; down: rows of y, next, y+51; columns of x-+12
+__device__ __forceinline__ bool ladder_probe(const LevelBlob &L, int px, int py, bool up) {
+    const int r0 = pad_cell(up ? py - 4 : py), r1 = up ? pad_cell(py) : min(pad_cell(py) + 1, pad_cell(py + 51)),
+              r2 = pad_cell(up ? py + 44 : py + 51);
+    const uint32_t m = L.row_ladder[r0] | L.row_ladder[r1] | L.row_ladder[r2];      // door cells never read LADDER
+    const bool hit = (((m >> pad_cell(px - 12)) | (m >> pad_cell(px + 12))) & 1u) != 0u;
+    return hit && (!up || py > 1);
 }
 
 // objs:46-53 evaluated at (px, py + 24): integer form of sqrt(dx^2 + dy^2) < r
@@ -259,32 +300,36 @@ template <bool TAPE, int NI>
 __device__ __forceinline__ void tick(Env<NI> &e, const LevelBlob &L, int act) {
     int xd = 0, yd = 0;
     e.total_actions++;
-    if (act == A_UP) {
-        if (can_go_up(L, e.flags, e.px, e.py)) yd = noisy<TAPE>(e, true);
-    } else if (act == A_DOWN) {
-        if (can_go_down(L, e.flags, e.px, e.py)) yd = noisy<TAPE>(e, false);
-    } else if (act == A_LEFT) {
-        if (side_free(L, e.flags, e.px - 16, e.py)) { xd = noisy<TAPE>(e, true); e.flags &= ~(1u << F_FACING); }
-    } else if (act == A_RIGHT) {
-        if (side_free(L, e.flags, e.px + 16, e.py)) { xd = noisy<TAPE>(e, false); e.flags |= 1u << F_FACING; }
+    if (act >= A_UP && act <= A_RIGHT) {
+        // impl:297-313.  One instruction stream for the four moves (lanes of a warp mix them):
+        // the move is permitted by the ladder probe (UP/DOWN) or the side probe (LEFT/RIGHT), then
+        // noisy() draws once; LEFT/RIGHT also set facing_right (unchanged when blocked).
+        const bool horiz = act >= A_LEFT, neg = (act == A_UP) || (act == A_LEFT);
+        const bool ok = horiz ? side_free_m(e, L, e.px + (neg ? -16 : 16)) : ladder_probe(L, e.px, e.py, neg);
+        if (ok) {
+            const int d = noisy<TAPE>(e, neg);
+            if (horiz) { xd = d; e.flags = (e.flags & ~(1u << F_FACING)) | (neg ? 0u : (1u << F_FACING)); }
+            else yd = d;
+        }
     } else if (act == A_JUMP) {
-        if (!can_go_down(L, e.flags, e.px, e.py) && up_clear(L, e.flags, e.px, e.py))
+        if (!ladder_probe(L, e.px, e.py, false) && up_clear(L, e.flags, e.px, e.py))
             e.flags = set_ticker(e.flags, draw_k<TAPE>(e) > (1ull << 51) ? 23 : 22);   // impl:316-319: random() > 0.25
     } else if (act == A_INTERACT) {
         interact<TAPE>(e, L);
+        e.m_py = INT_MIN;            // doors may have moved: drop the row-mask cache
     }
     int tk = ticker(e.flags);
     if (tk > 0) {                                                                    // impl:331-334
         if (up_clear(L, e.flags, e.px, e.py)) yd = -4;
         e.flags = set_ticker(e.flags, tk - 1);
-    } else if (can_fall(L, e.flags, e.px, e.py)) {                                   // impl:335-337
+    } else if (can_fall_m(e, L)) {                                                   // impl:335-337
         yd = 4;
     }
     e.px += xd;                                                                      // impl:339
-    if (yd > 0 && can_fall(L, e.flags, e.px, e.py)) {                                // impl:341-346
+    if (yd > 0 && can_fall_m(e, L)) {                                                // impl:341-346
         do {
             e.py++; yd--;
-            if (!can_fall(L, e.flags, e.px, e.py)) yd = 0;
+            if (!can_fall_m(e, L)) yd = 0;
         } while (yd > 0);
     } else {
         e.py += yd;                                                                  // impl:348
@@ -409,20 +454,20 @@ __device__ __forceinline__ int run_option_to_end(Env<NI> &e, const LevelBlob &L,
         if (k <= TG_GO_RIGHT) {                           // opts:74-85 / 146-157
             done = al; act = (s < 0) ? A_LEFT : A_RIGHT;
         } else if (k == TG_UP_LADDER) {                   // opts:168-173
-            done = !can_go_up(L, e.flags, e.px, e.py); act = done ? A_NOP : A_UP;
+            done = !ladder_probe(L, e.px, e.py, true); act = done ? A_NOP : A_UP;
         } else if (k == TG_DOWN_LADDER) {                 // opts:184-189
-            done = !can_go_down(L, e.flags, e.px, e.py); act = done ? A_NOP : A_DOWN;
+            done = !ladder_probe(L, e.px, e.py, false); act = done ? A_NOP : A_DOWN;
         } else if (k == TG_INTERACT) {                    // opts:457-460
             done = true; act = A_INTERACT;
         } else if (k <= TG_DOWN_RIGHT) {                  // opts:231-244 / 426-439
-            if (al) { done = !can_fall(L, e.flags, e.px, e.py); act = A_NOP; }
+            if (al) { done = !can_fall_m(e, L); act = A_NOP; }
             else act = (s < 0) ? A_LEFT : A_RIGHT;
         } else {                                          // opts:297-314 / 367-384
             if (n == 0) act = A_JUMP;
-            else if (al) { done = !can_fall(L, e.flags, e.px, e.py); act = A_NOP; }
+            else if (al) { done = !can_fall_m(e, L); act = A_NOP; }
             else {
-                bool blocked = !side_free(L, e.flags, e.px + 16 * s, e.py);
-                bool grounded = !can_fall(L, e.flags, e.px, e.py);
+                bool blocked = !side_free_m(e, L, e.px + 16 * s);
+                bool grounded = !can_fall_m(e, L);
                 bool rev = grounded && blocked;
                 act = ((s < 0) != rev) ? A_LEFT : A_RIGHT;
             }
@@ -571,6 +616,7 @@ __device__ __forceinline__ void load_env(Env<NI> &e, const BatchView &B, int64_t
         if (NI > 3) { e.ix[3] = lo16(h.y); e.iy[3] = hi16(h.y); }
     }
     e.draws = acct.x; e.total_actions = acct.w;
+    e.m_py = INT_MIN; e.m_fall = 0; e.m_side = 0;
     e.blk = 0xFFFFFFFFu; e.w0 = e.w1 = e.w2 = e.w3 = 0;
     e.key0 = B.seed_lo; e.key1 = B.seed_hi;
     uint64_t id = (uint64_t)(B.first_env_id + i);

@@ -50,6 +50,12 @@ struct alignas(16) LevelBlob {
     uint8_t trig_dst[TG_MAX_TRIGGERS];
     float inv_w, inv_h;                  // unused by parity paths (obs divides in double)
     uint32_t pad_[2];
+    // row bit masks over the padded columns (bit = column index + PAD), door cells cleared:
+    uint32_t row_nonopen[TSTRIDE];       // WALL or LADDER (anything but OPEN)          -> can_fall, up_clear
+    uint32_t row_solid[TSTRIDE];         // WALL                                          -> can_go_left/right
+    uint32_t row_ladder[TSTRIDE];        // LADDER                                        -> can_go_up/down
+    uint8_t row_lut[TSTRIDE];            // 0 = no door in this row, else 1 + index into door_lut
+    uint32_t door_lut[TG_MAX_DOORS][64]; // [rows with doors][closed-door bits] -> column bits of the closed doors of the row
 };
 static_assert(sizeof(LevelBlob) % 16 == 0, "LevelBlob must be a multiple of 16 bytes");
 
