@@ -180,6 +180,7 @@ extern "C" int tg_level_create(const uint8_t *tiles, int32_t cw, int32_t ch, con
     for (int r = 0; r < TSTRIDE; r++)
         for (int c = 0; c < TSTRIDE; c++) {
             const uint8_t code = b.tiles[r * TSTRIDE + c];
+            if (code & TC_STATIC_OBJ) b.row_static_obj[r] |= 1u << c;
             if (code & TC_HAS_DOOR) continue;
             const int t = code & 3;
             if (t != T_OPEN) b.row_nonopen[r] |= 1u << c;

@@ -354,7 +354,7 @@ __device__ __forceinline__ int floordiv48(int v) { return (v >= 0) ? v / S : -((
 
 template <int NI>
 __device__ __forceinline__ void player_cell(const Env<NI> &e, int &cx, int &cy) {   // impl:441-445
-    cx = floordiv48(e.px); cy = floordiv48(e.py + S / 2);
+    cx = pad_cell(e.px) - PAD; cy = pad_cell(e.py + S / 2) - PAD;     // exact floor: both arguments are >= -PAD*S
 }
 
 // impl:402-409 is_object_at: handle / bolt / key / gold in the cell, or a *closed* door
@@ -374,23 +374,34 @@ __device__ __forceinline__ bool closed_door_at(const LevelBlob &L, uint32_t flag
     return (code & TC_HAS_DOOR) && ((flags >> (F_DOORS + (code >> 4))) & 1u);
 }
 
-// go_left (s=-1) / go_right (s=+1): can_run + target column.  opts:23-67 / opts:95-139
+// go_left (s=-1) / go_right (s=+1): can_run + target column (opts:23-67 / opts:95-139) on row bit masks.
+// is_target_cell(xc) = ladder above/below | wall at xc+s | object at xc (handle, bolt, key, gold, closed
+// door) | closed door at xc+s | open cell below xc+s; the target is the first such column beyond the
+// player's; can_run = every cell from the player's to the target is OPEN over a non-OPEN cell.
 template <int NI>
 __device__ __forceinline__ bool walk_setup(const Env<NI> &e, const LevelBlob &L, int s, int &tcx) {
-    int pcx, pcy; player_cell(e, pcx, pcy);
     const uint32_t f = e.flags;
-    bool ok = type_c(L, f, pcx, pcy) == T_OPEN && type_c(L, f, pcx, pcy + 1) != T_OPEN;
-    int xc = pcx + s;
-    for (int it = 0; it < TSTRIDE + 2; it++) {
-        bool tgt = type_c(L, f, xc, pcy - 1) == T_LADDER || type_c(L, f, xc, pcy + 1) == T_LADDER
-                || type_c(L, f, xc + s, pcy) == T_WALL || object_at(e, L, xc, pcy)
-                || closed_door_at(L, f, xc + s, pcy) || type_c(L, f, xc + s, pcy + 1) == T_OPEN;
-        ok = ok && type_c(L, f, xc, pcy) == T_OPEN && type_c(L, f, xc, pcy + 1) != T_OPEN;
-        if (tgt) { tcx = xc; return ok; }
-        xc += s;
-        if (xc < 0) return false;                       // opts:49-50 -> None -> not runnable
+    const int cxp = pad_cell(e.px), r = pad_cell(e.py + S / 2);          // padded player cell
+    const uint32_t D = door_bits(L, f, r), D1 = door_bits(L, f, r + 1);  // closed doors of this row / the row below
+    const uint32_t open_r = ~(L.row_nonopen[r] | D), open_r1 = ~(L.row_nonopen[r + 1] | D1);
+    uint32_t obj = L.row_static_obj[r] | D;                              // impl:402-409
+#pragma unroll
+    for (int i = 0; i < NI; i++) {       // obj.cx/cy follow x/y (objs:34-44): C '/' truncates like int(x / 48)
+        const int icx = e.ix[i] / S + PAD, icy = e.iy[i] / S + PAD;
+        if (i < L.n_items && icy == r && icx >= 0 && icx < TSTRIDE) obj |= 1u << icx;
     }
-    return false;
+    const uint32_t nb = L.row_solid[r] | D | open_r1;                    // the three tests that look at column xc + s
+    const uint32_t tm = L.row_ladder[r - 1] | L.row_ladder[r + 1] | obj | (s < 0 ? nb << 1 : nb >> 1);
+    // candidates strictly beyond the player's column, inside the grid on the left (opts:49-50: xc < 0 -> None);
+    // on the right the border wall always yields a target
+    const uint32_t cand = s < 0 ? tm & ((1u << cxp) - 1u) & ~((1u << PAD) - 1u) : tm & ~((2u << cxp) - 1u);
+    if (!cand) return false;
+    const int txp = s < 0 ? 31 - __clz(cand) : __ffs(cand) - 1;
+    const uint32_t okm = open_r & ~open_r1;                              // opts:34-39
+    const int lo = min(cxp, txp), hi = max(cxp, txp);
+    const uint32_t range = ((2u << hi) - 1u) & ~((1u << lo) - 1u);
+    tcx = txp - PAD;
+    return (okm & range) == range;
 }
 
 __device__ __forceinline__ bool landing(const LevelBlob &L, uint32_t f, int cx, int cy) {   // opts:281-287
@@ -559,10 +570,14 @@ __device__ __forceinline__ void reset_env(Env<NI> &e, const LevelBlob &L) {
 // ---------------------------------------------------------------------------
 template <int NI>
 __device__ __forceinline__ void write_obs(const Env<NI> &e, const LevelBlob &L, float *o, int obs_dim) {
-    const double W = (double)(L.cw * S), H = (double)(L.ch * S);
+    // float(px) / width is computed in float64 by the reference and stored here as float32.  For these
+    // small integers the correctly rounded float32 quotient equals the float64 quotient rounded to float32
+    // (the quotient is a multiple of 1/(W*2^k) away from every rounding boundary, far more than 2^-53),
+    // so one IEEE float division gives the identical value (tests compare against the float64 oracle).
+    const float W = (float)(L.cw * S), H = (float)(L.ch * S);
     int k = 0;
-    o[k++] = (float)((double)e.px / W);
-    o[k++] = (float)((double)e.py / H);
+    o[k++] = __fdiv_rn((float)e.px, W);
+    o[k++] = __fdiv_rn((float)e.py, H);
     for (int j = 0; j < L.n_objs; j++) {
         int kind = L.obj_kind[j], i = L.obj_idx[j];
         if (kind == TG_HANDLE) o[k++] = (float)e.angles[(int64_t)i * e.n];
@@ -571,7 +586,7 @@ __device__ __forceinline__ void write_obs(const Env<NI> &e, const LevelBlob &L, 
             int x = 0, y = 0;
 #pragma unroll
             for (int q = 0; q < NI; q++) if (q == i) { x = e.ix[q]; y = e.iy[q]; }
-            o[k++] = (float)((double)x / W); o[k++] = (float)((double)y / H);
+            o[k++] = __fdiv_rn((float)x, W); o[k++] = __fdiv_rn((float)y, H);
         }
     }
     for (; k < obs_dim; k++) o[k] = 0.0f;

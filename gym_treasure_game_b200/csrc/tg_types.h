@@ -54,6 +54,7 @@ struct alignas(16) LevelBlob {
     uint32_t row_nonopen[TSTRIDE];       // WALL or LADDER (anything but OPEN)          -> can_fall, up_clear
     uint32_t row_solid[TSTRIDE];         // WALL                                          -> can_go_left/right
     uint32_t row_ladder[TSTRIDE];        // LADDER                                        -> can_go_up/down
+    uint32_t row_static_obj[TSTRIDE];    // a handle or bolt lives in the cell (is_object_at, impl:402-409)
     uint8_t row_lut[TSTRIDE];            // 0 = no door in this row, else 1 + index into door_lut
     uint32_t door_lut[TG_MAX_DOORS][64]; // [rows with doors][closed-door bits] -> column bits of the closed doors of the row
 };
