@@ -236,30 +236,29 @@ __device__ __forceinline__ void put_px(const Unit &u, int x, int y, int r, int g
     d[0] = (uint8_t)r; d[1] = (uint8_t)g; d[2] = (uint8_t)b;
 }
 
-// the column of a 48-wide sprite at ox that this thread owns (or -1)
-__device__ __forceinline__ int owned_col(int ox) {
-    int sx = ((int)threadIdx.x - 32 - ox) % RS_PATCH_THREADS;      // patch threads are tid 32..255
-    if (sx < 0) sx += RS_PATCH_THREADS;
-    return sx < S ? sx : -1;
-}
-
+// Pixel ownership among the 224 composer threads: owner(x, y) = (x + 48 * (y & 3)) mod 224.  Every
+// object touching a pixel is therefore applied by the same thread, in file order, with no barriers
+// between objects, and a 48-wide sprite spreads over 192 threads (2 rows each in an 8-row unit)
+// instead of 48 threads with 8 serial rows each.
 __device__ __forceinline__ void blit_cols(const Unit &u, const uint32_t *__restrict__ spr, int ox, int oy) {
     const int r0 = max(u.y0 - oy, 0), r1 = min(u.y0 + u.UR - oy, S);
     if (r0 >= r1) return;
-    const int sx = owned_col(ox);
-    if (sx < 0) return;
-    const int x = ox + sx;
+    int v = ((int)threadIdx.x - 32 - ox) % RS_PATCH_THREADS;       // patch threads are tid 32..255
+    if (v < 0) v += RS_PATCH_THREADS;
+    if (v >= 4 * S) return;
+    const int cls = v / S, sx = v - cls * S, x = ox + sx;
     if (x < 0 || x >= u.W) return;
-    for (int rb = r0; rb < r1; rb += 8) {            // 8 independent loads in flight, then 8 blends
-        uint32_t px8[8];
+    int sy = r0 + ((cls - (oy + r0)) & 3);                         // first row >= r0 with ((oy + sy) & 3) == cls
+    for (; sy < r1; sy += 16) {                                    // up to 4 rows of this class in flight
+        uint32_t px4[4];
 #pragma unroll
-        for (int q = 0; q < 8; q++) px8[q] = (rb + q < r1) ? __ldg(spr + (rb + q) * S + sx) : 0u;
+        for (int q = 0; q < 4; q++) px4[q] = (sy + 4 * q < r1) ? __ldg(spr + (sy + 4 * q) * S + sx) : 0u;
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const uint32_t s = px8[q];
+        for (int q = 0; q < 4; q++) {
+            const uint32_t s = px4[q];
             const int a = s >> 24;
-            if (a == 0) continue;                    // also skips the rows beyond r1
-            uint8_t *d = u.buf + ((oy + rb + q - u.y0) * u.W + x) * 3;
+            if (a == 0) continue;                                  // also skips rows beyond r1
+            uint8_t *d = u.buf + ((oy + sy + 4 * q - u.y0) * u.W + x) * 3;
             const int sr = s & 255, sg = (s >> 8) & 255, sb = (s >> 16) & 255;
             if (a == 255) { d[0] = (uint8_t)sr; d[1] = (uint8_t)sg; d[2] = (uint8_t)sb; }
             else {
@@ -308,28 +307,93 @@ __device__ __forceinline__ void lever_pixels(const Unit &u, int x1, int y1, int 
     }
 }
 
+// column ownership over n threads (my = this thread's index among them)
+__device__ __forceinline__ int owned_col_n(int ox, int my, int n) {
+    int sx = (my - ox) % n;
+    if (sx < 0) sx += n;
+    return sx < S ? sx : -1;
+}
+
+// blit_cols with an explicit owner set (used by all 256 threads when the static prefix is baked)
+__device__ __forceinline__ void blit_cols_n(const Unit &u, const uint32_t *__restrict__ spr, int ox, int oy, int my, int n) {
+    const int r0 = max(u.y0 - oy, 0), r1 = min(u.y0 + u.UR - oy, S);
+    if (r0 >= r1) return;
+    const int sx = owned_col_n(ox, my, n);
+    if (sx < 0) return;
+    const int x = ox + sx;
+    if (x < 0 || x >= u.W) return;
+    for (int rb = r0; rb < r1; rb += 8) {
+        uint32_t px8[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) px8[q] = (rb + q < r1) ? __ldg(spr + (rb + q) * S + sx) : 0u;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const uint32_t s = px8[q];
+            const int a = s >> 24;
+            if (a == 0) continue;
+            uint8_t *d = u.buf + ((oy + rb + q - u.y0) * u.W + x) * 3;
+            const int sr = s & 255, sg = (s >> 8) & 255, sb = (s >> 16) & 255;
+            if (a == 255) { d[0] = (uint8_t)sr; d[1] = (uint8_t)sg; d[2] = (uint8_t)sb; }
+            else {
+                const int dr = d[0], dg = d[1], db = d[2];
+                d[0] = (uint8_t)(dr + (((sr - dr) * a) >> 8));
+                d[1] = (uint8_t)(dg + (((sg - dg) * a) >> 8));
+                d[2] = (uint8_t)(db + (((sb - db) * a) >> 8));
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar_a, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar_a), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load(uint32_t dst_a, const void *src, uint32_t bytes, uint32_t bar_a) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_a), "l"(src), "r"(bytes), "r"(bar_a) : "memory");
+}
+__device__ __forceinline__ void tma_store(void *dst, uint32_t src_a, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_a), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// Per job the unit type (rows y0 .. y0+UR) is fixed, so the objects that can touch it are known.  The
+// leading run (file order) of two-state objects among them -- doors, bolts, keys/gold resting at their
+// initial cell -- is the *static prefix*: it is blitted once per job into C (the job's copy of the
+// pristine rows) in the state combination most envs of the job share (key K*).  Then
+//   mode 0: env's prefix state == K* and nothing else touches the rows  -> streamed straight from C
+//   mode 1: == K* but a lever / handle base / moved item / the hero touches the rows -> W = copy of C + those
+//   mode 2: prefix state differs from K*  -> W = pristine rows re-fetched by TMA (L2) + every object
+// Drawing order is preserved: everything outside the prefix comes later in file order, the hero last.
 __global__ void __launch_bounds__(RS_THREADS)
 tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int64_t first, int64_t count,
                         uint8_t *__restrict__ frames, int dbg) {
     extern __shared__ __align__(128) uint8_t rs_smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, bar2;
     __shared__ uint4 s_core[RS_EB];
     __shared__ uint2 s_items23[RS_EB];
     __shared__ short2 s_lever[RS_EB][TG_MAX_HANDLES];
     __shared__ int8_t disc_lo[32], disc_hi[32];
     __shared__ short4 s_obj[TG_MAX_OBJECTS];          // draw list: x = ox, y = oy, z = kind, w = index in kind
-    __shared__ int s_nobj, s_nhandles, s_nitems;
-    __shared__ uint8_t s_dirty[RS_EB];
+    __shared__ short2 s_item_init[TG_MAX_ITEMS];      // initial pixel position of every key / gold
+    __shared__ int s_nobj, s_nhandles, s_nitems, s_votes;
+    __shared__ uint16_t s_key[RS_EB];
+    __shared__ uint8_t s_mode[RS_EB];
     const int tid = threadIdx.x;
     const uint32_t unit_bytes = (uint32_t)(UR * W * 3);
-    uint8_t *P = rs_smem, *W0 = rs_smem + unit_bytes, *W1 = rs_smem + 2 * (size_t)unit_bytes;
-    const uint32_t bar_a = smem_addr(&bar);
+    uint8_t *C = rs_smem, *W0 = rs_smem + unit_bytes, *W1 = rs_smem + 2 * (size_t)unit_bytes;
+    const uint32_t bar_a = smem_addr(&bar), bar2_a = smem_addr(&bar2);
     const LevelBlob &L = B.levels[0];
     const uint32_t *spr = A.sprites;
     const int rad = S / 10;                                       // int(xscale / 10), drawer.py:265
 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar2_a));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_nobj = L.n_objs; s_nhandles = L.n_handles; s_nitems = L.n_items;
         for (int o = 0; o < L.n_objs; o++) {
@@ -338,6 +402,7 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int64
             if (kind == TG_DOOR) { cx = L.door_cx[i]; cy = L.door_cy[i]; }
             else if (kind == TG_BOLT) { cx = L.bolt_cx[i]; cy = L.bolt_cy[i]; }
             else if (kind == TG_HANDLE) { cx = L.handle_cx[i]; cy = L.handle_cy[i]; }
+            else { cx = L.item_cx[i]; cy = L.item_cy[i]; s_item_init[i] = make_short2((short)(cx * S), (short)(cy * S)); }
             s_obj[o] = make_short4((short)(cx * S), (short)(cy * S), (short)kind, (short)i);
         }
         // filled-circle spans of pygame 1.9.x draw_fillellipse(rx = ry = rad), recorded per row
@@ -361,21 +426,22 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int64
     const int ntypes = H / UR;
     const int nblocks = (int)((count + RS_EB - 1) / RS_EB);
     const int64_t njobs = (int64_t)ntypes * nblocks;
-    uint32_t parity = 0;
-    int G = 0, lastW[2] = {-1, -1}, nd = 0;          // bulk-group bookkeeping (meaningful on thread 0)
+    const int nobj = s_nobj;
+    uint32_t parity = 0, parity2 = 0;
+    int G = 0, lastW[2] = {-1, -1}, nd = 0;          // bulk-group bookkeeping of the composer's issuer (tid 32)
 
     for (int64_t job = blockIdx.x; job < njobs; job += gridDim.x) {
         const int t = (int)(job / nblocks), blk = (int)(job % nblocks);
         const int64_t e0 = (int64_t)blk * RS_EB;
         const int ne = (int)min((int64_t)RS_EB, count - e0);
         const int y0 = t * UR;
+        const uint8_t *pristine = A.background + (size_t)y0 * W * 3;
+        auto rows_hit = [&](int oy, int above, int below) { return oy + S + below > y0 && oy - above < y0 + UR; };
         if (tid == 0) {
-            wait_bulk_read(0);                       // every store that still reads P / W has drained
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(unit_bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_addr(P)), "l"(A.background + (size_t)y0 * W * 3), "r"(unit_bytes), "r"(bar_a) : "memory");
+            wait_bulk_read(0);                       // the streamer's stores out of C have drained
+            tma_load(smem_addr(C), pristine, unit_bytes, bar_a);
+            s_votes = 0;
         }
-        __syncthreads();                             // previous job's readers of s_core are done
         if (tid < ne) {
             const int64_t env = first + e0 + tid;
             s_core[tid] = B.core[env];
@@ -388,51 +454,100 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int64
                                                 (short)(int)__dsub_rn(syd, __dmul_rn(36.0, sin(th))));
             }
         }
-        __syncthreads();
-        uint32_t okw;
-        do {
-            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                         : "=r"(okw) : "r"(bar_a), "r"(parity) : "memory");
-        } while (!okw);
-        parity ^= 1u;
-        auto rows_hit = [&](int oy, int above, int below) { return oy + S + below > y0 && oy - above < y0 + UR; };
-        const int nobj = s_nobj, nitems = s_nitems;
-        bool static_dirty = false;                   // doors / bolts / handles sit at fixed rows: same for the whole job
+        // static prefix of this unit type (uniform): bit o of pre_mask = object o is baked into C
+        uint32_t pre_mask = 0;
         for (int o = 0; o < nobj; o++) {
             const short4 ob = s_obj[o];
-            if (ob.z == TG_DOOR || ob.z == TG_BOLT) static_dirty |= rows_hit(ob.y, 0, 0);
-            else if (ob.z == TG_HANDLE) static_dirty |= rows_hit(ob.y, 0, 3);
+            if (ob.z == TG_HANDLE) { if (rows_hit(ob.y, 0, 3)) break; else continue; }
+            if (rows_hit(ob.y, 0, 0)) pre_mask |= 1u << o;
         }
-
-        // which units of the job have anything dynamic in rows [y0, y0+UR)?
+        __syncthreads();                             // state block visible; s_votes reset
+        // prefix state of every env: door closed / bolt locked / item resting at its initial cell
+        bool item_moved_here = false;                // an item away from its initial cell touches these rows
         if (tid < ne) {
             const uint4 c = s_core[tid];
             const uint32_t items[4] = {c.z, c.w, s_items23[tid].x, s_items23[tid].y};
-            bool dirty = static_dirty || rows_hit(hi16(c.x), 0, 0);
+            uint32_t key = 0;
+            for (int o = 0; o < nobj; o++) {
+                const short4 ob = s_obj[o];
+                bool bit = false;
+                if (ob.z == TG_DOOR) bit = (c.y >> (F_DOORS + ob.w)) & 1u;
+                else if (ob.z == TG_BOLT) bit = (c.y >> (F_BOLTS + ob.w)) & 1u;
+                else if (ob.z != TG_HANDLE) {
+                    uint32_t it = items[0];
 #pragma unroll
-            for (int q = 0; q < TG_MAX_ITEMS; q++) dirty |= q < nitems && lo16(items[q]) >= 0 && rows_hit(hi16(items[q]), 0, 0);
-            s_dirty[tid] = (dirty && dbg != 1) ? 1 : 0;     // dbg: timing experiments only (TG_RENDER_DBG)
+                    for (int q = 1; q < TG_MAX_ITEMS; q++) if (q == ob.w) it = items[q];
+                    bit = lo16(it) == ob.x && hi16(it) == ob.y;
+                    if (!bit && lo16(it) >= 0 && rows_hit(hi16(it), 0, 0)) item_moved_here = true;
+                }
+                if (bit && ((pre_mask >> o) & 1u)) key |= 1u << o;
+            }
+            s_key[tid] = (uint16_t)key;
+        }
+        __syncthreads();
+        if (tid < ne) {                              // majority vote for K*
+            int cnt = 0;
+            const uint16_t mine = s_key[tid];
+            for (int v = 0; v < ne; v++) cnt += (s_key[v] == mine);
+            atomicMax(&s_votes, (cnt << 16) | tid);
+        }
+        __syncthreads();
+        const uint32_t kstar = s_key[s_votes & 0xFFFF];
+        mbar_wait(bar_a, parity);                    // pristine rows have landed in C
+        parity ^= 1u;
+        {   // bake the prefix in state K* into C (all 256 threads, column-owned, file order)
+            Unit u; u.buf = C; u.W = W; u.y0 = y0; u.UR = UR;
+            for (int o = 0; o < nobj; o++) {
+                if (!((pre_mask >> o) & 1u)) continue;
+                const short4 ob = s_obj[o];
+                const bool bit = (kstar >> o) & 1u;
+                const uint32_t *sp = nullptr;
+                if (ob.z == TG_DOOR) sp = spr + (bit ? TG_SPR_DOOR_CLOSED : TG_SPR_DOOR_OPEN) * S * S;
+                else if (ob.z == TG_BOLT) sp = spr + (bit ? TG_SPR_BOLT_LOCKED : TG_SPR_BOLT_OPEN) * S * S;
+                else if (bit) sp = spr + (ob.z == TG_KEY ? TG_SPR_KEY : TG_SPR_GOLD) * S * S;
+                if (sp) blit_cols_n(u, sp, ob.x, ob.y, tid, RS_THREADS);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (tid < ne) {
+            const uint4 c = s_core[tid];
+            bool dyn = rows_hit(hi16(c.x), 0, 0) || item_moved_here;           // hero, moved items
+            for (int o = 0; o < nobj; o++) {                                     // objects outside the prefix
+                const short4 ob = s_obj[o];
+                if ((pre_mask >> o) & 1u) continue;
+                if (ob.z == TG_HANDLE) dyn |= rows_hit(ob.y, 0, 3);
+                else if (ob.z == TG_DOOR || ob.z == TG_BOLT) dyn |= rows_hit(ob.y, 0, 0);
+                // items outside the prefix: resting ones count if their cell touches the rows, moved ones are in item_moved_here
+                else {
+                    const uint32_t items[4] = {c.z, c.w, s_items23[tid].x, s_items23[tid].y};
+                    uint32_t it = items[0];
+#pragma unroll
+                    for (int q = 1; q < TG_MAX_ITEMS; q++) if (q == ob.w) it = items[q];
+                    dyn |= lo16(it) >= 0 && rows_hit(hi16(it), 0, 0);
+                }
+            }
+            const bool same = s_key[tid] == (uint16_t)kstar && !item_moved_here;
+            s_mode[tid] = (dbg == 1) ? 0 : (!same ? 2 : (dyn ? 1 : 0));
         }
         __syncthreads();
         uint8_t *job_dst = frames + ((size_t)e0 * H + (size_t)y0) * (size_t)W * 3;
         const size_t frame_bytes = (size_t)H * W * 3;
 
         if (tid < 32) {
-            // ---- role 1 (warp 0): stream the clean units straight from the pristine rows ----
+            // ---- role 1 (warp 0): stream the units that are exactly C ----
             if (tid == 0) {
                 for (int uidx = 0; uidx < ne; uidx++) {
-                    if (s_dirty[uidx]) continue;
+                    if (s_mode[uidx] != 0) continue;
                     wait_bulk_read(6);
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 ::"l"(job_dst + uidx * frame_bytes), "r"(smem_addr(P)), "r"(unit_bytes) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    tma_store(job_dst + uidx * frame_bytes, smem_addr(C), unit_bytes);
                 }
             }
         } else {
-            // ---- role 2 (warps 1..7): compose the dirty units in W0/W1 and store them ----
+            // ---- role 2 (warps 1..7): compose the other units in W0/W1 and store them ----
             const int pt = tid - 32;
             for (int uidx = 0; uidx < ne; uidx++) {
-                if (!s_dirty[uidx]) continue;
+                const int mode = s_mode[uidx];
+                if (mode == 0) continue;
                 const uint4 c = s_core[uidx];
                 const uint32_t f = c.y;
                 const int px = lo16(c.x), py = hi16(c.x);
@@ -440,16 +555,23 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int64
                 const int kbuf = nd & 1;
                 nd++;
                 uint8_t *wbuf = kbuf ? W1 : W0;
-                if (pt == 0 && lastW[kbuf] >= 0) wait_bulk_read(min(G - 1 - lastW[kbuf], 6));
+                if (pt == 0) {
+                    if (lastW[kbuf] >= 0) wait_bulk_read(min(G - 1 - lastW[kbuf], 6));
+                    if (mode == 2) tma_load(smem_addr(wbuf), pristine, unit_bytes, bar2_a);
+                }
                 patch_barrier();
-                {   // working copy <- pristine rows
-                    const uint4 *src4 = reinterpret_cast<const uint4 *>(P);
+                if (mode == 2) {
+                    mbar_wait(bar2_a, parity2);
+                } else {                             // working copy <- C
+                    const uint4 *src4 = reinterpret_cast<const uint4 *>(C);
                     uint4 *dst4 = reinterpret_cast<uint4 *>(wbuf);
                     for (uint32_t q = pt; q < unit_bytes / 16; q += RS_PATCH_THREADS) dst4[q] = src4[q];
                 }
+                if (mode == 2) parity2 ^= 1u;
                 patch_barrier();
                 Unit u; u.buf = wbuf; u.W = W; u.y0 = y0; u.UR = UR;
-                for (int o = 0; o < ((dbg == 2 || dbg == 3) ? 0 : nobj); o++) {                      // drawer.py:154-155
+                for (int o = 0; o < nobj; o++) {                                       // drawer.py:154-155
+                    if (mode == 1 && ((pre_mask >> o) & 1u)) continue;                 // already in C
                     const short4 ob = s_obj[o];
                     const int kind = ob.z, i = ob.w;
                     if (kind == TG_DOOR) {
@@ -465,7 +587,7 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int64
                         const bool locked = (f >> (F_BOLTS + i)) & 1u;
                         blit_cols(u, spr + (locked ? TG_SPR_BOLT_LOCKED : TG_SPR_BOLT_OPEN) * S * S, ob.x, ob.y);
                     } else {
-                        if (rows_hit(ob.y, 0, 3) && dbg != 4) {    // lever rows: oy+8 .. oy+50 (uniform branch)
+                        if (rows_hit(ob.y, 0, 3)) {    // lever rows: oy+8 .. oy+50 (uniform branch)
                             patch_barrier();
                             lever_pixels(u, ob.x + S / 2, ob.y + S, s_lever[uidx][i].x, s_lever[uidx][i].y, rad, disc_lo, disc_hi);
                             patch_barrier();
@@ -473,23 +595,21 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int64
                         blit_cols(u, spr + TG_SPR_HANDLE_BASE * S * S, ob.x, ob.y);
                     }
                 }
-                if (dbg != 2 && dbg != 5) blit_cols(u, spr + ((f & 1u) ? TG_SPR_HERO_RIGHT : TG_SPR_HERO_LEFT) * S * S, px - S / 2, py);   // drawer.py:157-161
+                blit_cols(u, spr + ((f & 1u) ? TG_SPR_HERO_RIGHT : TG_SPR_HERO_LEFT) * S * S, px - S / 2, py);   // drawer.py:157-161
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 patch_barrier();
                 if (pt == 0) {
                     wait_bulk_read(6);
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 ::"l"(job_dst + uidx * frame_bytes), "r"(smem_addr(wbuf)), "r"(unit_bytes) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    tma_store(job_dst + uidx * frame_bytes, smem_addr(wbuf), unit_bytes);
                     lastW[kbuf] = G;
                     G++;
                 }
             }
         }
-        __syncthreads();                             // both roles are done with P before the next job reloads it
+        __syncthreads();                             // both roles are done with C before the next job reloads it
     }
-    if (tid == 32) wait_bulk_read(0);                // (the composer's issuer; the streamer's follows)
-    if (tid == 0) wait_bulk_read(0);                 // shared memory must outlive the last bulk store's reads
+    if (tid == 32) wait_bulk_read(0);                // shared memory must outlive the last bulk stores' reads
+    if (tid == 0) wait_bulk_read(0);
 }
 
 static bool g_render_configured = false;
@@ -509,14 +629,14 @@ cudaError_t render_configure() {
     return e;
 }
 
-// rows per unit of the streaming renderer: the largest divisor of 48 whose three buffers fit four times per
-// SM (measured on B200, 16384 frames of 672x624: UR 6/8/12/16/24 -> 4.48/4.68/4.46/4.23/2.70 TB/s)
+// rows per unit of the streaming renderer: the largest divisor of 48 whose three buffers fit three times per
+// SM (measured on B200, 16384 frames of 672x624, final kernel: UR 6/8/12/16/24 -> 4.84/5.00/5.19/5.08/4.09 TB/s)
 static int pick_unit_rows(int W) {
     static int forced = -1;
     if (forced < 0) { const char *v = getenv("TG_RENDER_UR"); forced = v ? atoi(v) : 0; }
     if (forced > 0 && 48 % forced == 0) return forced;
     static const int cand[] = {48, 24, 16, 12, 8, 6, 4};
-    for (int ur : cand) if ((size_t)3 * ur * W * 3 <= 54 * 1024) return ur;
+    for (int ur : cand) if ((size_t)3 * ur * W * 3 <= 74 * 1024) return ur;
     return 4;
 }
 
