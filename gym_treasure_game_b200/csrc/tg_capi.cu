@@ -63,6 +63,9 @@ struct tg_env {
     int32_t *s_actions = nullptr; float *s_obs = nullptr; float *s_reward = nullptr;
     uint8_t *s_done = nullptr; uint8_t *s_ran = nullptr;
     int64_t launches = 0;
+    // tg_step_host pipeline: step kernel of chunk c+1 overlaps the device->host copies of chunk c
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_chunk[8] = {}, ev_join = nullptr;
 };
 
 extern "C" const char *tg_last_error(void) { return g_err; }
@@ -238,6 +241,9 @@ static cudaError_t dev_alloc(tg_env *e, T **p, size_t count) {
 
 static void free_env(tg_env *e) {
     if (!e) return;
+    if (e->side) cudaStreamDestroy(e->side);
+    for (cudaEvent_t ev : e->ev_chunk) if (ev) cudaEventDestroy(ev);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     for (void *p : e->allocs) cudaFree(p);
     delete e;
 }
@@ -267,6 +273,7 @@ extern "C" int tg_create(const tg_level *const *levels, int32_t n_levels, const 
     e->device = device; e->n_levels = n_levels;
     BatchView &B = e->B;
     B.n = num_envs; B.first_env_id = first_env_id; B.n_levels = n_levels;
+    B.r_begin = 0; B.r_count = num_envs;
     B.max_steps = max_episode_steps; B.auto_reset = auto_reset ? 1 : 0;
     B.seed_lo = (uint32_t)seed; B.seed_hi = (uint32_t)(seed >> 32);
     int max_items = 0, obs_dim = 0;
@@ -377,15 +384,42 @@ extern "C" int tg_step_host(tg_env *env, const int32_t *actions, float *obs, flo
     int rc = ensure_staging(env);
     if (rc != TG_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t n = (size_t)env->B.n;
-    CU(cudaMemcpyAsync(env->s_actions, actions, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    CU(launch_step(env->B, env->ni, env->s_actions, obs ? env->s_obs : nullptr, reward ? env->s_reward : nullptr,
-                   done ? env->s_done : nullptr, ran ? env->s_ran : nullptr, nullptr, s));
-    env->launches++;
-    if (obs) CU(cudaMemcpyAsync(obs, env->s_obs, n * env->B.obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (reward) CU(cudaMemcpyAsync(reward, env->s_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (done) CU(cudaMemcpyAsync(done, env->s_done, n, cudaMemcpyDeviceToHost, s));
-    if (ran) CU(cudaMemcpyAsync(ran, env->s_ran, n, cudaMemcpyDeviceToHost, s));
+    const int64_t n = env->B.n;
+    const int od = env->B.obs_dim;
+    // Large batches are split into chunks: while the copy engine drains chunk c's results over PCIe,
+    // the SMs already run chunk c+1.  Env ranges are independent, so the result is the same as one launch.
+    int chunks = 1;
+    if (n >= (int64_t)4 * 131072) chunks = 4; else if (n >= (int64_t)2 * 131072) chunks = 2;
+    if (chunks > 1 && !env->side) {
+        CU(cudaStreamCreateWithFlags(&env->side, cudaStreamNonBlocking));
+        for (int c = 0; c < 8; c++) CU(cudaEventCreateWithFlags(&env->ev_chunk[c], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&env->ev_join, cudaEventDisableTiming));
+    }
+    CU(cudaMemcpyAsync(env->s_actions, actions, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    const int64_t per = ((n + chunks - 1) / chunks + 2047) / 2048 * 2048;      // tile-aligned chunk size
+    for (int c = 0; c < chunks; c++) {
+        const int64_t lo = (int64_t)c * per, cnt = (lo + per <= n) ? per : n - lo;
+        if (cnt <= 0) break;
+        BatchView V = env->B;
+        V.r_begin = lo; V.r_count = cnt;
+        CU(launch_step(V, env->ni, env->s_actions, obs ? env->s_obs : nullptr, reward ? env->s_reward : nullptr,
+                       done ? env->s_done : nullptr, ran ? env->s_ran : nullptr, nullptr, s));
+        env->launches++;
+        cudaStream_t cs = s;
+        if (chunks > 1) {
+            CU(cudaEventRecord(env->ev_chunk[c], s));
+            CU(cudaStreamWaitEvent(env->side, env->ev_chunk[c], 0));
+            cs = env->side;
+        }
+        if (obs) CU(cudaMemcpyAsync(obs + lo * od, env->s_obs + lo * od, (size_t)cnt * od * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        if (reward) CU(cudaMemcpyAsync(reward + lo, env->s_reward + lo, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        if (done) CU(cudaMemcpyAsync(done + lo, env->s_done + lo, (size_t)cnt, cudaMemcpyDeviceToHost, cs));
+        if (ran) CU(cudaMemcpyAsync(ran + lo, env->s_ran + lo, (size_t)cnt, cudaMemcpyDeviceToHost, cs));
+    }
+    if (chunks > 1) {
+        CU(cudaEventRecord(env->ev_join, env->side));
+        CU(cudaStreamWaitEvent(s, env->ev_join, 0));
+    }
     CU(cudaStreamSynchronize(s));
     return TG_OK;
 }

@@ -44,7 +44,10 @@ __device__ __forceinline__ void stats_accumulate(int *sh, unsigned long long *gs
         atomicAdd(&gstats[threadIdx.x], (unsigned long long)(long long)sh[threadIdx.x]);
 }
 
-constexpr int STEP_THREADS = 256;
+#ifndef TG_STEP_THREADS
+#define TG_STEP_THREADS 256
+#endif
+constexpr int STEP_THREADS = TG_STEP_THREADS;
 constexpr int AUX_THREADS = 128;       // reset / mask kernels
 constexpr int NBUCKET = 64;          // length classes for the in-tile sort (bucket 0 = longest, 63 = not runnable)
 
@@ -87,8 +90,8 @@ tg_step_kernel(BatchView B, const int32_t *__restrict__ actions, float *__restri
     if (tid == 0) next_chunk = 0;
     stage_levels(levels, B.levels, B.n_levels, &bar);      // contains a __syncthreads()
 
-    const int64_t base = (int64_t)blockIdx.x * TILE;
-    const int count = (int)min((int64_t)TILE, B.n - base);
+    const int64_t base = B.r_begin + (int64_t)blockIdx.x * TILE;
+    const int count = (int)min((int64_t)TILE, B.r_begin + B.r_count - base);
 
     // ---- phase 1: classify ------------------------------------------------
     for (int el = tid; el < count; el += STEP_THREADS) {
@@ -288,7 +291,7 @@ static inline size_t level_smem(const BatchView &B) { return (size_t)B.n_levels 
 template <bool TAPE, int NI, int TILE>
 static cudaError_t step_tile(const BatchView &B, const int32_t *a, float *obs, float *rew, uint8_t *done,
                              uint8_t *ran, uint16_t *avail, cudaStream_t s) {
-    tg_step_kernel<TAPE, NI, TILE><<<grid_for(B.n, TILE), STEP_THREADS, level_smem(B), s>>>(B, a, obs, rew, done, ran, avail);
+    tg_step_kernel<TAPE, NI, TILE><<<grid_for(B.r_count, TILE), STEP_THREADS, level_smem(B), s>>>(B, a, obs, rew, done, ran, avail);
     return cudaGetLastError();
 }
 
@@ -319,7 +322,7 @@ int pick_step_tile(int64_t n) {
 cudaError_t launch_step(const BatchView &B, int ni, const int32_t *a, float *obs, float *rew, uint8_t *done,
                         uint8_t *ran, uint16_t *avail, cudaStream_t s) {
     const bool tape = B.tape != nullptr;
-    const int tile = pick_step_tile(B.n);
+    const int tile = pick_step_tile(B.r_count);
     if (ni <= 2) return tape ? step_impl<true, 2>(B, tile, a, obs, rew, done, ran, avail, s) : step_impl<false, 2>(B, tile, a, obs, rew, done, ran, avail, s);
     return tape ? step_impl<true, 4>(B, tile, a, obs, rew, done, ran, avail, s) : step_impl<false, 4>(B, tile, a, obs, rew, done, ran, avail, s);
 }

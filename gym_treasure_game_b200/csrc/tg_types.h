@@ -67,6 +67,7 @@ enum : int { ST_EPISODES = 0, ST_SUCCESS, ST_RETURN, ST_EPSTEPS, ST_TICKS, ST_RA
 struct BatchView {
     int64_t n;
     int64_t first_env_id;
+    int64_t r_begin, r_count;   // env range one step launch covers ([0, n) unless tg_step_host pipelines chunks)
     uint4 *core;          // [N]  x=pos(px | py<<16)  y=flags  z=item0 (x | y<<16)  w=item1
     uint4 *acct;          // [N]  x=draws  y=ep_return  z=ep_steps  w=total_actions
     uint2 *items23;       // [N]  items 2,3 (NULL when every level has <= 2 items)

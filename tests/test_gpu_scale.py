@@ -71,3 +71,22 @@ def test_render_16384_frames_properties():
         a, b = int(order[j]), int(order[j + 1])
         if all(torch.equal(full[k][a], full[k][b]) for k in ("misc", "doors", "handles", "bolts", "angles", "items")):
             assert torch.equal(frames[a], frames[b])
+
+
+@pytest.mark.parametrize("n", [300001, 600000])
+def test_pipelined_host_step_equals_single_launch(n):
+    """tg_step_host splits large batches into chunks (kernel of chunk c+1 overlaps the D2H of chunk c);
+    env ranges are independent, so the outputs must equal one whole-batch launch."""
+    from gym_treasure_game_b200 import VectorTreasureGame
+    e1 = VectorTreasureGame(n, seed=21, max_episode_steps=25, render=False)
+    e2 = VectorTreasureGame(n, seed=21, max_episode_steps=25, render=False)
+    host = e2.make_host_buffers()
+    g = torch.Generator().manual_seed(8)
+    for _ in range(30):
+        a = torch.randint(0, 9, (n,), generator=g, dtype=torch.int32)
+        o, r, d, ran = e1.step_raw(a.cuda())
+        host["actions"].copy_(a)
+        e2.step_host(host)
+        assert torch.equal(o.cpu(), host["obs"]) and torch.equal(r.cpu(), host["reward"])
+        assert torch.equal(d.cpu(), host["done"]) and torch.equal(ran.cpu(), host["ran"])
+    assert e1.stats() == e2.stats()
