@@ -459,6 +459,14 @@ extern "C" int tg_set_state(tg_env *env, const tg_state_view *in, void *stream) 
     return TG_OK;
 }
 
+extern "C" int tg_init_with_state(tg_env *env, const double *states, const uint8_t *mask, void *stream) {
+    if (!env || !states) return fail(TG_ERR_ARG, "null argument");
+    DeviceGuard guard(env->device);
+    CU(launch_init_with_state(env->B, env->ni, states, mask, (cudaStream_t)stream));
+    env->launches++;
+    return TG_OK;
+}
+
 extern "C" int tg_set_draw_tape(tg_env *env, const double *tape, const int64_t *offsets, void *stream) {
     if (!env) return fail(TG_ERR_ARG, "null env");
     if ((tape == nullptr) != (offsets == nullptr)) return fail(TG_ERR_ARG, "tape and offsets must both be set or both be null");

@@ -21,6 +21,7 @@ template <int NI>
 struct Env {
     int px, py;
     uint32_t flags;
+    uint32_t sticky;             // per handle: previously_triggered left raised by init_with_state (impl:473)
     int ix[NI], iy[NI];          // item (key / gold) pixel positions
     uint32_t draws;              // uniforms consumed by this env since creation
     uint32_t total_actions;      // impl:53,295 (per episode)
@@ -43,7 +44,15 @@ __device__ __forceinline__ int ticker(uint32_t f) { return (f >> F_TICKER) & 31u
 __device__ __forceinline__ uint32_t set_ticker(uint32_t f, int t) {
     return (f & ~(31u << F_TICKER)) | ((uint32_t)t << F_TICKER);
 }
-__device__ __forceinline__ int bag_len(uint32_t f) { return __popc((f >> F_INBAG) & ((1u << TG_MAX_ITEMS) - 1)); }
+__device__ __forceinline__ int bag_len(uint32_t f) { return (f >> F_BAGLEN) & 7u; }
+// set of item indices present in the bag (impl:418-428 player_got_key / player_got_goldcoin)
+__device__ __forceinline__ uint32_t bag_items(uint32_t f) {
+    const int len = bag_len(f);
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < TG_MAX_ITEMS; j++) if (j < len) m |= 1u << ((f >> (F_BAGORD + 2 * j)) & 3u);
+    return m;
+}
 
 // ---------------------------------------------------------------------------
 // RNG: Philox4x32-10, two 53-bit uniforms per block (same construction as
@@ -190,8 +199,8 @@ __device__ __forceinline__ bool near_px(int px, int py, int ox, int oy, int r2) 
     return dx * dx + dy * dy < r2;
 }
 
-__device__ __forceinline__ bool has_key(const LevelBlob &L, uint32_t f) { return ((f >> F_INBAG) & L.key_mask) != 0; }
-__device__ __forceinline__ bool has_gold(const LevelBlob &L, uint32_t f) { return ((f >> F_INBAG) & L.gold_mask) != 0; }
+__device__ __forceinline__ bool has_key(const LevelBlob &L, uint32_t f) { return (bag_items(f) & L.key_mask) != 0; }
+__device__ __forceinline__ bool has_gold(const LevelBlob &L, uint32_t f) { return (bag_items(f) & L.gold_mask) != 0; }
 
 // ---------------------------------------------------------------------------
 // trigger graph + INTERACT (rare: one tick per interact option) -- kept out of line
@@ -214,14 +223,17 @@ __device__ __forceinline__ bool apply_val(Env<NI> &e, const LevelBlob &L, int o,
     return true;
 }
 
-// set_val + recursive process_trigger (objs:76-94) as an explicit DFS.  `pt` is the set of
-// objects whose previously_triggered flag is raised (those on the DFS stack).
+// process_trigger (objs:76-94) as an explicit DFS from object o0 that has just taken value v0.  `pt` is the
+// set of objects whose previously_triggered flag is raised: those on the DFS stack plus the handles that
+// init_with_state left flagged (impl:473, Env::sticky); a flag is lowered when its object's own
+// process_trigger returns (objs:94), which is also how a sticky flag eventually clears.
 template <bool TAPE, int NI>
-__device__ __forceinline__ void set_val(Env<NI> &e, const LevelBlob &L, int o0, bool v0) {
-    if (!apply_val<TAPE>(e, L, o0, v0)) return;
+__device__ __forceinline__ void trigger_dfs(Env<NI> &e, const LevelBlob &L, int o0, bool v0) {
     uint8_t st_src[TG_MAX_OBJECTS], st_t[TG_MAX_OBJECTS];
     int sp = 0;
-    uint32_t pt = 1u << o0;
+    uint32_t pt = 0;
+    for (int h = 0; h < L.n_handles; h++) if ((e.sticky >> h) & 1u) pt |= 1u << L.handle_obj[h];
+    pt |= 1u << o0;
     st_src[0] = (uint8_t)(o0 | (v0 ? 128 : 0)); st_t[0] = 0; sp = 1;
     while (sp > 0) {
         int src = st_src[sp - 1], t = st_t[sp - 1];
@@ -241,6 +253,15 @@ __device__ __forceinline__ void set_val(Env<NI> &e, const LevelBlob &L, int o0, 
         }
         if (!pushed) { pt &= ~(1u << (src & 127)); sp--; }         // objs:94
     }
+    uint32_t sticky = 0;
+    for (int h = 0; h < L.n_handles; h++) if ((pt >> L.handle_obj[h]) & 1u) sticky |= 1u << h;
+    e.sticky = sticky;
+}
+
+// set_val (objs:145-149, :175-178, :231-235): nothing happens unless the value changes
+template <bool TAPE, int NI>
+__device__ __forceinline__ void set_val(Env<NI> &e, const LevelBlob &L, int o0, bool v0) {
+    if (apply_val<TAPE>(e, L, o0, v0)) trigger_dfs<TAPE>(e, L, o0, v0);
 }
 
 // impl:434-439: the first key in bag order leaves the bag and goes to cell (-1,-1)
@@ -255,7 +276,7 @@ __device__ __forceinline__ void drop_key(Env<NI> &e, const LevelBlob &L) {
             uint32_t high = (ord >> (2 * j + 2)) << (2 * j);
             ord = (low | high) & 0xFFu;
             e.flags = (e.flags & ~(0xFFu << F_BAGORD)) | (ord << F_BAGORD);
-            e.flags &= ~(1u << (F_INBAG + it));
+            e.flags = (e.flags & ~(7u << F_BAGLEN)) | ((uint32_t)(len - 1) << F_BAGLEN);   // player_bag.remove(obj)
 #pragma unroll
             for (int q = 0; q < NI; q++) if (q == it) { e.ix[q] = -S; e.iy[q] = -S; }
             return;
@@ -339,10 +360,14 @@ __device__ __forceinline__ void tick(Env<NI> &e, const LevelBlob &L, int act) {
 #pragma unroll
     for (int i = 0; i < NI; i++) {
         if (i < L.n_items && near_px(e.px, e.py, e.ix[i], e.iy[i], 24 * 24)) {
-            int len = bag_len(e.flags);
+            const int len = bag_len(e.flags);
             e.ix[i] = bx - len * S; e.iy[i] = by;                                    // objs:34-38
-            e.flags |= 1u << (F_INBAG + i);
-            e.flags = (e.flags & ~(3u << (F_BAGORD + 2 * len))) | ((uint32_t)i << (F_BAGORD + 2 * len));
+            if (len < TG_MAX_ITEMS) {                                                // player_bag.append(obj)
+                e.flags = (e.flags & ~(3u << (F_BAGORD + 2 * len))) | ((uint32_t)i << (F_BAGORD + 2 * len));
+                e.flags = (e.flags & ~(7u << F_BAGLEN)) | ((uint32_t)(len + 1) << F_BAGLEN);
+            } else {
+                e.flags |= 1u << F_ERROR;     // a fifth bag entry (only reachable through repeated re-pickups) is not representable
+            }
         }
     }
 }
@@ -546,6 +571,7 @@ __device__ __forceinline__ uint32_t available_bits(const Env<NI> &e, const Level
 template <bool TAPE, int NI>
 __device__ __forceinline__ void reset_env(Env<NI> &e, const LevelBlob &L) {
     e.flags = L.init_flags | (e.flags & (1u << F_ERROR));      // the error flag is sticky until tg_reset
+    e.sticky = 0;                                              // fresh objects (impl:57-60)
     for (int h = 0; h < L.n_handles; h++) {
         bool up = (L.init_flags >> (F_HANDLES + h)) & 1u;
         e.angles[(int64_t)h * e.n] = handle_angle(up, draw<TAPE>(e));
@@ -598,9 +624,64 @@ __device__ __forceinline__ bool is_done(const Env<NI> &e, const LevelBlob &L) { 
 }
 
 // ---------------------------------------------------------------------------
+// init_with_state (impl:447-481) with its quirks: -99 keeps the current value through a float64 round trip
+// (int(float(px)/W*W) can lose a pixel), every key / gold / bolt reads the FIRST slot carrying its name
+// (desc.index), facing is forced right, bag / ticker / total_actions are untouched, handle.set_angle
+// propagates triggers (objs:133-143; targets redraw their angle) and leaves the handle flagged.
+// ---------------------------------------------------------------------------
+template <bool TAPE, int NI>
+__device__ void init_with_state_env(Env<NI> &e, const LevelBlob &L, const double *__restrict__ in) {
+    const double W = (double)(L.cw * S), H = (double)(L.ch * S);
+    double st[2 + 2 * TG_MAX_OBJECTS];
+    int first_key = -1, first_gold = -1, first_bolt = -1;
+    st[0] = (double)e.px / W; st[1] = (double)e.py / H;                   // impl:368-378 (current vector)
+    for (int o = 0; o < L.n_objs; o++) {
+        const int kind = L.obj_kind[o], i = L.obj_idx[o], k = L.obj_obs[o];
+        if (kind == TG_HANDLE) st[k] = e.angles[(int64_t)i * e.n];
+        else if (kind == TG_BOLT) { st[k] = ((e.flags >> (F_BOLTS + i)) & 1u) ? 1.0 : 0.0; if (first_bolt < 0) first_bolt = k; }
+        else if (kind == TG_KEY || kind == TG_GOLD) {
+            int x = 0, y = 0;
+#pragma unroll
+            for (int q = 0; q < NI; q++) if (q == i) { x = e.ix[q]; y = e.iy[q]; }
+            st[k] = (double)x / W; st[k + 1] = (double)y / H;
+            if (kind == TG_KEY) { if (first_key < 0) first_key = k; } else if (first_gold < 0) first_gold = k;
+        }
+    }
+    for (int v = 0; v < L.obs_dim; v++) { const double g = in[v]; if (g != -99.0) st[v] = g; }
+    e.flags |= 1u << F_FACING;
+    e.px = (int)__dmul_rn(st[0], W); e.py = (int)__dmul_rn(st[1], H);
+    e.px = min(max(e.px, 0), L.cw * S - 1); e.py = min(max(e.py, -(S - 1)), L.ch * S - 1);   // probe invariants
+    for (int o = 0; o < L.n_objs; o++) {
+        const int kind = L.obj_kind[o], i = L.obj_idx[o], k = L.obj_obs[o];
+        if (kind == TG_KEY || kind == TG_GOLD) {                             // objs:40-44 move_to_xy
+            const int slot = (kind == TG_KEY) ? first_key : first_gold;
+            const int x = (int)__dmul_rn(st[slot], W), y = (int)__dmul_rn(st[slot + 1], H);
+#pragma unroll
+            for (int q = 0; q < NI; q++) if (q == i) { e.ix[q] = x; e.iy[q] = y; }
+        } else if (kind == TG_HANDLE) {                                      // objs:133-143 set_angle
+            const double ang = st[k];
+            const bool old = (e.flags >> (F_HANDLES + i)) & 1u, up = !(ang <= 0.15);
+            e.angles[(int64_t)i * e.n] = ang;
+            e.flags = (e.flags & ~(1u << (F_HANDLES + i))) | ((up ? 1u : 0u) << (F_HANDLES + i));
+            if (up != old) trigger_dfs<TAPE>(e, L, o, up);
+            e.sticky |= 1u << i;                                             // impl:473
+        } else if (kind == TG_BOLT) {
+            set_val<TAPE>(e, L, o, st[first_bolt] > 0.5);
+        }
+    }
+    e.m_py = INT_MIN;
+}
+
+// ---------------------------------------------------------------------------
 // packed state <-> registers
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_xy(int x, int y) { return ((uint32_t)x & 0xFFFFu) | ((uint32_t)y << 16); }
+// core.x = playerx (12 bits, 0 <= x < 26*48) | sticky handle flags (4 bits) | playery << 16
+__device__ __forceinline__ uint32_t pack_player(int px, int py, uint32_t sticky) {
+    return ((uint32_t)px & 0xFFFu) | ((sticky & 15u) << 12) | ((uint32_t)py << 16);
+}
+__device__ __forceinline__ int core_px(uint32_t v) { return (int)(v & 0xFFFu); }
+__device__ __forceinline__ uint32_t core_sticky(uint32_t v) { return (v >> 12) & 15u; }
 __device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xFFFFu); }
 __device__ __forceinline__ int hi16(uint32_t v) { return (int)(int16_t)(v >> 16); }
 
@@ -608,7 +689,7 @@ __device__ __forceinline__ int hi16(uint32_t v) { return (int)(int16_t)(v >> 16)
 template <int NI>
 __device__ __forceinline__ void load_core(Env<NI> &e, const BatchView &B, int64_t i) {
     uint4 c = B.core[i];
-    e.px = lo16(c.x); e.py = hi16(c.x); e.flags = c.y;
+    e.px = core_px(c.x); e.py = hi16(c.x); e.sticky = core_sticky(c.x); e.flags = c.y;
     e.ix[0] = lo16(c.z); e.iy[0] = hi16(c.z);
     if (NI > 1) { e.ix[1] = lo16(c.w); e.iy[1] = hi16(c.w); }
     if (NI > 2) {
@@ -622,7 +703,7 @@ template <int NI>
 __device__ __forceinline__ void load_env(Env<NI> &e, const BatchView &B, int64_t i, uint4 &acct) {
     uint4 c = B.core[i];
     acct = B.acct[i];
-    e.px = lo16(c.x); e.py = hi16(c.x); e.flags = c.y;
+    e.px = core_px(c.x); e.py = hi16(c.x); e.sticky = core_sticky(c.x); e.flags = c.y;
     e.ix[0] = lo16(c.z); e.iy[0] = hi16(c.z);
     if (NI > 1) { e.ix[1] = lo16(c.w); e.iy[1] = hi16(c.w); }
     if (NI > 2) {
@@ -643,7 +724,7 @@ __device__ __forceinline__ void load_env(Env<NI> &e, const BatchView &B, int64_t
 template <int NI>
 __device__ __forceinline__ void store_env(const Env<NI> &e, const BatchView &B, int64_t i, uint4 acct) {
     uint4 c;
-    c.x = pack_xy(e.px, e.py); c.y = e.flags;
+    c.x = pack_player(e.px, e.py, e.sticky); c.y = e.flags;
     c.z = pack_xy(e.ix[0], e.iy[0]);
     c.w = (NI > 1) ? pack_xy(e.ix[1], e.iy[1]) : 0u;
     B.core[i] = c;

@@ -130,7 +130,7 @@ tg_render_band_kernel(BatchView B, RenderView R, int64_t first, uint8_t *__restr
     // env state (uniform across the CTA) while the band is in flight
     const uint4 c = B.core[env];
     const uint32_t f = c.y;
-    const int px = lo16(c.x), py = hi16(c.x);
+    const int px = core_px(c.x), py = hi16(c.x);
     uint32_t items[4] = {c.z, c.w, 0u, 0u};
     if (B.items23) { const uint2 h = B.items23[env]; items[2] = h.x; items[3] = h.y; }
     __syncthreads();
@@ -550,7 +550,7 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int64
                 if (mode == 0) continue;
                 const uint4 c = s_core[uidx];
                 const uint32_t f = c.y;
-                const int px = lo16(c.x), py = hi16(c.x);
+                const int px = core_px(c.x), py = hi16(c.x);
                 const uint32_t items[4] = {c.z, c.w, s_items23[uidx].x, s_items23[uidx].y};
                 const int kbuf = nd & 1;
                 nd++;

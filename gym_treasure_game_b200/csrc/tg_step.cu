@@ -214,13 +214,30 @@ tg_mask_kernel(BatchView B, uint8_t *__restrict__ mask) {
     for (int k = 0; k < TG_NUM_OPTIONS; k++) mask[i * TG_NUM_OPTIONS + k] = (m >> k) & 1u;
 }
 
+template <bool TAPE, int NI>
+__global__ void __launch_bounds__(AUX_THREADS)
+tg_init_with_state_kernel(BatchView B, const double *__restrict__ states, const uint8_t *__restrict__ mask) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LevelBlob *levels = reinterpret_cast<LevelBlob *>(smem_raw);
+    __shared__ uint64_t bar;
+    stage_levels(levels, B.levels, B.n_levels, &bar);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.n || (mask && !mask[i])) return;
+    const LevelBlob &L = levels[B.level_id ? B.level_id[i] : 0];
+    Env<NI> e;
+    uint4 acct;
+    load_env(e, B, i, acct);
+    init_with_state_env<TAPE>(e, L, states + i * B.obs_dim);
+    store_env(e, B, i, acct);
+}
+
 // ---- state get / set (unpacked view, strides = TG_MAX_*) -------------------
 __global__ void tg_get_state_kernel(BatchView B, tg_state_view v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B.n) return;
     const uint4 c = B.core[i], a = B.acct[i];
     const uint32_t f = c.y;
-    if (v.pos) { v.pos[i * 2] = lo16(c.x); v.pos[i * 2 + 1] = hi16(c.x); }
+    if (v.pos) { v.pos[i * 2] = core_px(c.x); v.pos[i * 2 + 1] = hi16(c.x); }
     if (v.misc) { v.misc[i * 4] = f & 1u; v.misc[i * 4 + 1] = ticker(f); v.misc[i * 4 + 2] = (int)a.w; v.misc[i * 4 + 3] = (int)a.x; }
     if (v.doors) for (int j = 0; j < TG_MAX_DOORS; j++) v.doors[i * TG_MAX_DOORS + j] = (f >> (F_DOORS + j)) & 1u;
     if (v.handles) for (int j = 0; j < TG_MAX_HANDLES; j++) v.handles[i * TG_MAX_HANDLES + j] = (f >> (F_HANDLES + j)) & 1u;
@@ -233,7 +250,7 @@ __global__ void tg_get_state_kernel(BatchView B, tg_state_view v) {
         const int len = bag_len(f);
         for (int j = 0; j < TG_MAX_ITEMS; j++) v.bag[i * TG_MAX_ITEMS + j] = (j < len) ? (int)((f >> (F_BAGORD + 2 * j)) & 3u) : -1;
     }
-    if (v.acct) { v.acct[i * 3] = (int)a.y; v.acct[i * 3 + 1] = a.z; v.acct[i * 3 + 2] = (f >> F_ERROR) & 1u; }
+    if (v.acct) { v.acct[i * 3] = (int)a.y; v.acct[i * 3 + 1] = a.z; v.acct[i * 3 + 2] = ((f >> F_ERROR) & 1u) | (core_sticky(c.x) << 1); }
 }
 
 __global__ void tg_set_state_kernel(BatchView B, tg_state_view v) {
@@ -244,7 +261,7 @@ __global__ void tg_set_state_kernel(BatchView B, tg_state_view v) {
     if (v.pos) {   // keep the probe invariants of tg_device.cuh (pad_cell has no clamps)
         const LevelBlob &L = B.levels[B.level_id ? B.level_id[i] : 0];
         const int x = min(max(v.pos[i * 2], 0), L.cw * S - 1), y = min(max(v.pos[i * 2 + 1], -(S - 1)), L.ch * S - 1);
-        c.x = pack_xy(x, y);
+        c.x = pack_player(x, y, core_sticky(c.x));
     }
     if (v.misc) {
         f = (f & ~1u) | (v.misc[i * 4] ? 1u : 0u);
@@ -266,17 +283,20 @@ __global__ void tg_set_state_kernel(BatchView B, tg_state_view v) {
         }
     }
     if (v.bag) {
-        f &= ~(0xFFFu << F_INBAG);
+        f &= ~(0xFFFu << F_BAGLEN);
+        int len = 0;
         for (int j = 0; j < TG_MAX_ITEMS; j++) {
             int it = v.bag[i * TG_MAX_ITEMS + j];
             if (it < 0 || it >= TG_MAX_ITEMS) break;
-            f |= 1u << (F_INBAG + it);
             f |= (uint32_t)it << (F_BAGORD + 2 * j);
+            len++;
         }
+        f |= (uint32_t)len << F_BAGLEN;
     }
     if (v.acct) {
         a.y = (uint32_t)(int)v.acct[i * 3]; a.z = (uint32_t)v.acct[i * 3 + 1];
-        f = (f & ~(1u << F_ERROR)) | ((v.acct[i * 3 + 2] ? 1u : 0u) << F_ERROR);
+        f = (f & ~(1u << F_ERROR)) | (((v.acct[i * 3 + 2] & 1) ? 1u : 0u) << F_ERROR);
+        c.x = pack_player(core_px(c.x), hi16(c.x), (uint32_t)(v.acct[i * 3 + 2] >> 1));
     }
     c.y = f;
     B.core[i] = c; B.acct[i] = a;
@@ -337,6 +357,20 @@ cudaError_t launch_reset(const BatchView &B, int ni, const uint8_t *mask, float 
     } else {
         if (tape) tg_reset_kernel<true, 4><<<g, AUX_THREADS, sm, s>>>(B, mask, obs);
         else tg_reset_kernel<false, 4><<<g, AUX_THREADS, sm, s>>>(B, mask, obs);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_init_with_state(const BatchView &B, int ni, const double *states, const uint8_t *mask, cudaStream_t s) {
+    const unsigned g = grid_for(B.n, AUX_THREADS);
+    const size_t sm = level_smem(B);
+    const bool tape = B.tape != nullptr;
+    if (ni <= 2) {
+        if (tape) tg_init_with_state_kernel<true, 2><<<g, AUX_THREADS, sm, s>>>(B, states, mask);
+        else tg_init_with_state_kernel<false, 2><<<g, AUX_THREADS, sm, s>>>(B, states, mask);
+    } else {
+        if (tape) tg_init_with_state_kernel<true, 4><<<g, AUX_THREADS, sm, s>>>(B, states, mask);
+        else tg_init_with_state_kernel<false, 4><<<g, AUX_THREADS, sm, s>>>(B, states, mask);
     }
     return cudaGetLastError();
 }

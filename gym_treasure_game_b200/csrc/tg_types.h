@@ -26,8 +26,11 @@ constexpr int F_ERROR = 6;                        // 1 bit
 constexpr int F_DOORS = 7;                        // TG_MAX_DOORS bits, 1 = closed
 constexpr int F_HANDLES = F_DOORS + TG_MAX_DOORS; // 13, TG_MAX_HANDLES bits, 1 = up
 constexpr int F_BOLTS = F_HANDLES + TG_MAX_HANDLES; // 17, TG_MAX_BOLTS bits, 1 = locked
-constexpr int F_INBAG = F_BOLTS + TG_MAX_BOLTS;   // 20, TG_MAX_ITEMS bits
-constexpr int F_BAGORD = F_INBAG + TG_MAX_ITEMS;  // 24, TG_MAX_ITEMS x 2 bits: item index at bag position j
+// the bag is an ordered list that may hold an item twice (the reference appends on every pickup, impl:350-354,
+// and init_with_state can put a bagged item back on the map): length + TG_MAX_ITEMS slots of 2 bits
+constexpr int F_BAGLEN = F_BOLTS + TG_MAX_BOLTS;  // 20, 3 bits: entries in the bag (0..TG_MAX_ITEMS)
+constexpr int F_SPARE = F_BAGLEN + 3;             // 23, 1 bit unused
+constexpr int F_BAGORD = F_SPARE + 1;             // 24, TG_MAX_ITEMS x 2 bits: item index at bag position j
 static_assert(F_BAGORD + 2 * TG_MAX_ITEMS == 32, "flags word is exactly 32 bits");
 
 // One level, as staged in shared memory.  sizeof is a multiple of 16 (cp.async.bulk).

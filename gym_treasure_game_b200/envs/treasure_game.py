@@ -82,6 +82,16 @@ class TreasureGame(_EnvBase):
                 v += [float(items[it][0]) / W, float(items[it][1]) / H]; it += 1
         return v
 
+    # -- save / restore (the reference keeps these on ``env._env``: impl:368-400, 447-481) -------
+    def get_state(self):
+        return self._state_vector()
+
+    def get_state_descriptors(self):
+        return self.level.state_descriptors()
+
+    def init_with_state(self, state):
+        self._vec.init_with_state([list(state)])
+
     # -- gym API ------------------------------------------------------------------
     def reset(self):
         self._vec.reset()

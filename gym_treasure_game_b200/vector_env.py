@@ -227,6 +227,16 @@ class VectorTreasureGame:
         check(self._L.tg_set_state(self._h, C.byref(v), self._stream()))
         torch.cuda.current_stream(self.device).synchronize()
 
+    def init_with_state(self, states, mask: Optional[torch.Tensor] = None) -> None:
+        """``_TreasureGameImpl.init_with_state`` (impl:447-481) for every env (or ``mask != 0``):
+        ``states`` (N, obs_dim) float64 normalised vectors in ``Level.state_descriptors()`` order,
+        ``-99`` keeps the current value.  Reference quirks are reproduced (see treasure_b200.h)."""
+        st = torch.as_tensor(states, dtype=torch.float64).to(self.device).reshape(self.num_envs, self.obs_dim).contiguous()
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        check(self._L.tg_init_with_state(self._h, _ptr(st), _ptr(mask), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+
     def snapshot(self, i: int = 0, state: Optional[Dict[str, torch.Tensor]] = None) -> dict:
         """State of env ``i`` in the dict layout of the oracle snapshots (tests)."""
         s = state or self.get_state()
@@ -239,7 +249,8 @@ class VectorTreasureGame:
             doors=[int(v) for v in c["doors"][: info.n_doors]], handles_up=[int(v) for v in c["handles"][: info.n_handles]],
             angles=[float(v) for v in c["angles"][: info.n_handles]], bolts=[int(v) for v in c["bolts"][: info.n_bolts]],
             items=[(int(x), int(y), int(np.trunc(x / 48)), int(np.trunc(y / 48))) for x, y in c["items"][:ni]],
-            bag=[int(v) for v in c["bag"][:ni] if v >= 0], total_actions=int(c["misc"][2]))
+            bag=[int(v) for v in c["bag"] if v >= 0], total_actions=int(c["misc"][2]),
+            handles_pt=[(int(c["acct"][2]) >> (1 + h)) & 1 for h in range(info.n_handles)])
 
     def set_draw_tape(self, tapes: Optional[Sequence[Sequence[float]]]) -> None:
         """Parity mode: env i consumes ``tapes[i]`` (uniform draws recorded from the reference)

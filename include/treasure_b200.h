@@ -97,7 +97,7 @@ typedef struct {
     double  *angles;    /* [N][TG_MAX_HANDLES]                                       */
     int32_t *items;     /* [N][TG_MAX_ITEMS][2] x, y in pixels                       */
     int32_t *bag;       /* [N][TG_MAX_ITEMS]    item index per bag slot, -1 = empty  */
-    int64_t *acct;      /* [N][3]  episode return, episode steps, error flag         */
+    int64_t *acct;      /* [N][3]  episode return, episode steps, error flag | sticky handle flags << 1 */
 } tg_state_view;
 
 const char *tg_last_error(void);
@@ -161,6 +161,13 @@ int tg_render(tg_env *env, int64_t first, int64_t count, uint8_t *frames, void *
 /* State save / restore on the SoA (test hook; superset of impl:368-378 / :447-481). */
 int tg_get_state(tg_env *env, const tg_state_view *out, void *stream);
 int tg_set_state(tg_env *env, const tg_state_view *in, void *stream);
+
+/* _TreasureGameImpl.init_with_state (_treasure_game_impl.py:447-481), quirks included: states DEV [N][obs_dim]
+ * float64 normalised state vectors in get_state_descriptors order (:380-400), -99 = keep the current value;
+ * every key / gold / bolt reads the first slot of its name; facing is forced right; the bag, the jump ticker and
+ * the counters are untouched; handle angles propagate their triggers (targets redraw their angle from the env's
+ * RNG stream) and the handles stay flagged previously_triggered.  mask DEV [N] or NULL = all. */
+int tg_init_with_state(tg_env *env, const double *states, const uint8_t *mask, void *stream);
 
 /* Parity mode: uniform draws come from tape[offsets[i] + draw_index_i] instead of Philox.
  * Both DEV, must stay valid until replaced; (NULL, NULL) returns to Philox.  Resets draw indices to 0. */

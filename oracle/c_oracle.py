@@ -46,6 +46,8 @@ def lib():
         L.tgo_batch_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.tgo_batch_get.argtypes = [C.c_void_p] + [C.c_void_p] * 9
         L.tgo_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tgo_batch_init_with_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tgo_batch_get_pt.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -127,6 +129,16 @@ class CBatch:
         """No per-call allocations (for timing)."""
         lib().tgo_batch_step(self.h, _p(actions), None, _p(rew), _p(done), None, None)
 
+    def init_with_state(self, states, mask=None):
+        st = np.ascontiguousarray(states, dtype=np.float64).reshape(self.n, self.level.obs_dim)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        lib().tgo_batch_init_with_state(self.h, _p(st), _p(m))
+
+    def handles_pt(self):
+        pt = np.zeros((self.n, max(self.level.nh, 1)), dtype=np.uint8)
+        lib().tgo_batch_get_pt(self.h, _p(pt))
+        return pt[:, : self.level.nh]
+
     def mask(self):
         m = np.zeros((self.n, 9), dtype=np.uint8)
         lib().tgo_batch_mask(self.h, _p(m))
@@ -143,7 +155,7 @@ class CBatch:
             pos=np.zeros((n, 2), np.int32), misc=np.zeros((n, 4), np.int32),
             doors=np.zeros((n, max(lv.nd, 1)), np.uint8), handles=np.zeros((n, max(lv.nh, 1)), np.uint8),
             bolts=np.zeros((n, max(lv.nb, 1)), np.uint8), angles=np.zeros((n, max(lv.nh, 1)), np.float64),
-            items=np.zeros((n, max(lv.ni, 1), 4), np.int32), bag=np.full((n, max(lv.ni, 1)), -1, np.int32),
+            items=np.zeros((n, max(lv.ni, 1), 4), np.int32), bag=np.full((n, 4), -1, np.int32),
             acct=np.zeros((n, 3), np.int64))
         lib().tgo_batch_get(self.h, _p(out["pos"]), _p(out["misc"]), _p(out["doors"]), _p(out["handles"]),
                             _p(out["bolts"]), _p(out["angles"]), _p(out["items"]), _p(out["bag"]), _p(out["acct"]))
@@ -152,7 +164,6 @@ class CBatch:
         out["bolts"] = out["bolts"][:, : lv.nb]
         out["angles"] = out["angles"][:, : lv.nh]
         out["items"] = out["items"][:, : lv.ni]
-        out["bag"] = out["bag"][:, : lv.ni]
         return out
 
     def snapshot(self, i=0):
@@ -163,4 +174,5 @@ class CBatch:
             ticker=int(s["misc"][i, 1]), doors=[int(v) for v in s["doors"][i]],
             handles_up=[int(v) for v in s["handles"][i]], angles=[float(v) for v in s["angles"][i]],
             bolts=[int(v) for v in s["bolts"][i]], items=[tuple(int(v) for v in it) for it in s["items"][i]],
-            bag=[int(v) for v in s["bag"][i] if v >= 0], total_actions=int(s["misc"][i, 2]))
+            bag=[int(v) for v in s["bag"][i] if v >= 0], total_actions=int(s["misc"][i, 2]),
+            handles_pt=[int(v) for v in self.handles_pt()[i]])

@@ -488,6 +488,56 @@ class OracleEnv:
         r = self.run_option(a)
         return self.obs(), r, self.is_done(), {}
 
+    # ---- save / restore (impl:380-400, impl:447-481) ----------------------
+    def state_descriptors(self):
+        d = ["playerx", "playery"]
+        hn = 1
+        for o in self.objects:
+            if o.kind == K_HANDLE:
+                d.append("handle%d.angle" % hn)
+                hn += 1
+            elif o.kind == K_BOLT:
+                d.append("bolt.locked")
+            elif o.kind == K_KEY:
+                d += ["key.x", "key.y"]
+            elif o.kind == K_GOLD:
+                d += ["goldcoin.x", "goldcoin.y"]
+        return d
+
+    def init_with_state(self, state):
+        """impl:447-481, quirks included: -99 keeps the current value (through a float round trip
+        that can lose a pixel), every key / gold / bolt reads the FIRST slot of its name
+        (``desc.index``), facing is forced right, the bag and the jump ticker are untouched,
+        ``handle.set_angle`` propagates triggers (targets redraw their angle), and the handles keep
+        ``previously_triggered = True`` afterwards (impl:473; the reset at :479-481 hits the env)."""
+        desc = self.state_descriptors()
+        state = list(state)
+        self.facing = True
+        st = self.obs()
+        for v in range(len(st)):
+            if state[v] == -99:
+                state[v] = st[v]
+        self.px = int(state[desc.index("playerx")] * self.width)
+        self.py = int(state[desc.index("playery")] * self.height)
+        hn = 1
+        for o in self.objects:
+            if o.kind in (K_KEY, K_GOLD):
+                name = "key" if o.kind == K_KEY else "goldcoin"
+                o.x = int(state[desc.index(name + ".x")] * self.width)        # objs:40-44 move_to_xy
+                o.y = int(state[desc.index(name + ".y")] * self.height)
+                o.cx, o.cy = int(o.x / S), int(o.y / S)
+            elif o.kind == K_HANDLE:
+                angle = state[desc.index("handle%d.angle" % hn)]
+                old = o.val                                                   # objs:133-143 set_angle
+                o.angle = angle
+                o.val = not (angle <= 0.15)
+                if o.val != old:
+                    self._fire(o, o.val)
+                o.pt = True
+                hn += 1
+            elif o.kind == K_BOLT:
+                self._set_val(o, state[desc.index("bolt.locked")] > 0.5)
+
     # ---- full snapshot for differential tests -----------------------------
     def snapshot(self):
         items = [o for o in self.objects if o.kind in (K_KEY, K_GOLD)]
@@ -499,7 +549,8 @@ class OracleEnv:
             bolts=[int(o.val) for o in self.objects if o.kind == K_BOLT],
             items=[(o.x, o.y, o.cx, o.cy) for o in items],
             bag=[items.index(o) for o in self.bag],
-            total_actions=self.total_actions)
+            total_actions=self.total_actions,
+            handles_pt=[int(o.pt) for o in self.objects if o.kind == K_HANDLE])
 
 
 # --------------------------------------------------------------------------

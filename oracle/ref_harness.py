@@ -164,6 +164,7 @@ def impl_snapshot(env) -> dict:
     doors = [int(d.closed) for d in env.doors]
     handles_up = [int(h.up) for h in env.handles]
     angles = [float(h.angle) for h in env.handles]
+    handles_pt = [int(h.previously_triggered) for h in env.handles]
     bolts = [int(b.locked) for b in env.bolts]
     items = [(int(x.x), int(x.y), int(x.cx), int(x.cy)) for x in env.objects
              if isinstance(x, (o.key, o.goldcoin))]
@@ -172,7 +173,7 @@ def impl_snapshot(env) -> dict:
     return dict(px=int(env.playerx), py=int(env.playery),
                 facing=int(env.facing_right), ticker=int(env.jump_ticker),
                 doors=doors, handles_up=handles_up, angles=angles, bolts=bolts,
-                items=items, bag=bag, total_actions=int(env.total_actions))
+                items=items, bag=bag, total_actions=int(env.total_actions), handles_pt=handles_pt)
 
 
 class RefGame:

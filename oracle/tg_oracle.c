@@ -491,6 +491,50 @@ static int is_done(const env_t *e)                         /* tg:95 */
     return bag_has(e, K_GOLD) && yc == 0;
 }
 
+/* ----------------------------------------------------- save / restore ---- */
+/* impl:447-481 init_with_state, quirks included (see py_oracle.OracleEnv.init_with_state):
+ * every key / gold / bolt reads the FIRST slot carrying its name (desc.index), -99 keeps the current
+ * value through a float round trip, handles keep previously_triggered = True afterwards. */
+static void env_init_with_state(const batch_t *b, env_t *e, const double *in)
+{
+    const level_t *lv = e->lv;
+    double st[2 + 2 * MAXOBJ], cur[2 + 2 * MAXOBJ];
+    int od = lv->obs_dim;
+    int first_key = -1, first_gold = -1, first_bolt = -1, k = 2;
+    double W = lv->cw * S, H = lv->ch * S;
+    write_obs(e, cur);
+    for (int i = 0; i < lv->nobj; i++) {           /* slot of the first object of each name (impl:380-400) */
+        int kind = lv->obj[i].kind;
+        if (kind == K_HANDLE) k += 1;
+        else if (kind == K_BOLT) { if (first_bolt < 0) first_bolt = k; k += 1; }
+        else if (kind == K_KEY) { if (first_key < 0) first_key = k; k += 2; }
+        else if (kind == K_GOLD) { if (first_gold < 0) first_gold = k; k += 2; }
+    }
+    for (int v = 0; v < od; v++) st[v] = (in[v] == -99) ? cur[v] : in[v];
+    e->facing = 1;
+    e->px = (int)(st[0] * W); e->py = (int)(st[1] * H);
+    k = 2;
+    for (int i = 0; i < lv->nobj; i++) {
+        obj_t *o = &e->o[i];
+        if (o->kind == K_KEY || o->kind == K_GOLD) {
+            int slot = (o->kind == K_KEY) ? first_key : first_gold;
+            o->x = (int)(st[slot] * W); o->y = (int)(st[slot + 1] * H);        /* objs:40-44 move_to_xy */
+            o->cx = (int)(o->x / (double)S); o->cy = (int)(o->y / (double)S);
+            k += 2;
+        } else if (o->kind == K_HANDLE) {
+            int old = o->val;                                                  /* objs:133-143 set_angle */
+            o->angle = st[k];
+            o->val = !(o->angle <= 0.15);
+            if (o->val != old) fire(b, e, i, o->val);
+            o->pt = 1;                                                         /* impl:473 */
+            k += 1;
+        } else if (o->kind == K_BOLT) {
+            set_val(b, e, i, st[first_bolt] > 0.5);
+            k += 1;
+        }
+    }
+}
+
 /* --------------------------------------------------------------- batch ---- */
 void *tgo_batch_new(const void *level, int64_t n, int64_t first_env_id, uint64_t seed,
                     int max_episode_steps, int auto_reset)
@@ -554,6 +598,23 @@ void tgo_batch_step(void *bp, const int32_t *actions, double *obs, float *reward
     b->stats[4] += s4; b->stats[5] += s5; b->stats[6] += b->n; b->stats[7] += s7;
 }
 
+void tgo_batch_init_with_state(void *bp, const double *states, const uint8_t *mask)
+{
+    batch_t *b = bp; int od = b->lv->obs_dim;
+    for (int64_t i = 0; i < b->n; i++)
+        if (!mask || mask[i]) env_init_with_state(b, &b->e[i], states + i * od);
+}
+
+/* previously_triggered flag of every handle, [N][n_handles] */
+void tgo_batch_get_pt(void *bp, uint8_t *pt)
+{
+    batch_t *b = bp; const level_t *lv = b->lv; int nh = lv->n_of_kind[K_HANDLE];
+    for (int64_t i = 0; i < b->n; i++) {
+        int h = 0;
+        for (int j = 0; j < lv->nobj; j++) if (b->e[i].o[j].kind == K_HANDLE) pt[i * nh + h++] = (uint8_t)b->e[i].o[j].pt;
+    }
+}
+
 void tgo_batch_mask(void *bp, uint8_t *mask)               /* tg:83-89 */
 {
     batch_t *b = bp;
@@ -565,7 +626,8 @@ void tgo_batch_stats(void *bp, int64_t *out8) { memcpy(out8, ((batch_t *)bp)->st
 
 /* Flat state dump for differential tests.  Any pointer may be NULL.
  * pos[N*2]=px,py; misc[N*4]=facing,ticker,total_actions,draws; doors/handles/bolts[N*count] 0/1;
- * angles[N*nh]; items[N*ni*4]=x,y,cx,cy; bag[N*ni] item index or -1; acct[N*3]=ep_return,ep_steps,error */
+ * angles[N*nh]; items[N*ni*4]=x,y,cx,cy; bag[N*4] item index per bag slot or -1 (an item can appear twice);
+ * acct[N*3]=ep_return,ep_steps,error */
 void tgo_batch_get(void *bp, int32_t *pos, int32_t *misc, uint8_t *doors, uint8_t *handles,
                    uint8_t *bolts, double *angles, int32_t *items, int32_t *bag, int64_t *acct)
 {
@@ -585,7 +647,7 @@ void tgo_batch_get(void *bp, int32_t *pos, int32_t *misc, uint8_t *doors, uint8_
             else if (o->kind == K_BOLT) { if (bolts) bolts[i * nb + bo] = (uint8_t)o->val; bo++; }
             else { item_no[j] = c; if (items) { int32_t *p = items + (i * ni + c) * 4; p[0] = o->x; p[1] = o->y; p[2] = o->cx; p[3] = o->cy; } c++; }
         }
-        if (bag) for (int j = 0; j < ni; j++) bag[i * ni + j] = (j < e->nbag) ? item_no[e->bag[j]] : -1;
+        if (bag) for (int j = 0; j < 4; j++) bag[i * 4 + j] = (j < e->nbag) ? item_no[e->bag[j]] : -1;
         if (acct) { acct[i * 3] = e->ep_return; acct[i * 3 + 1] = e->ep_steps; acct[i * 3 + 2] = e->error; }
     }
 }

@@ -24,8 +24,14 @@ def assert_state_equal(env, cb, msg=""):
     np.testing.assert_array_equal(st["bolts"][:, : lv.nb], cs["bolts"], err_msg="bolts " + msg)
     np.testing.assert_array_equal(st["angles"][:, : lv.nh], cs["angles"], err_msg="angles (f64 bit-exact) " + msg)
     np.testing.assert_array_equal(st["items"][:, : lv.ni], cs["items"][:, :, :2], err_msg="items " + msg)
-    np.testing.assert_array_equal(st["bag"][:, : lv.ni], cs["bag"], err_msg="bag " + msg)
-    np.testing.assert_array_equal(st["acct"], cs["acct"], err_msg="episode accounting " + msg)
+    np.testing.assert_array_equal(st["bag"], cs["bag"], err_msg="bag (ordered, duplicates allowed) " + msg)
+    acct = st["acct"].copy()
+    sticky = acct[:, 2] >> 1
+    acct[:, 2] &= 1
+    np.testing.assert_array_equal(acct, cs["acct"], err_msg="episode accounting " + msg)
+    pt = cb.handles_pt()
+    np.testing.assert_array_equal(np.stack([(sticky >> h) & 1 for h in range(lv.nh)], axis=1) if lv.nh else pt, pt,
+                                  err_msg="sticky previously_triggered flags " + msg)
 
 
 def assert_step_equal(out, ref, msg=""):

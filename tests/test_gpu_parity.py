@@ -35,6 +35,12 @@ def test_cuda_replays_reference_golden(VTG, path):
     a = torch.zeros(1, dtype=torch.int32, device="cuda")
     for t, st in enumerate(rec["steps"]):
         assert env.available_mask[0].tolist() == st["mask"], t
+        if "restore" in st:                         # impl:447-481 init_with_state, quirks included
+            env.init_with_state([st["restore"]])
+            state = env.get_state()
+            assert env.snapshot(0, state) == norm_snap(st["snap"]), t
+            assert int(state["misc"][0, 3]) == st["draws"], t
+            continue
         a[0] = st["a"]
         obs, rew, done, info = env.step(a, want_available=True)
         state = env.get_state()
@@ -44,7 +50,7 @@ def test_cuda_replays_reference_golden(VTG, path):
         np.testing.assert_array_equal(obs[0].cpu().numpy(), np.asarray(st["obs"], dtype=np.float32), err_msg=str(t))
         assert env.snapshot(0, state) == norm_snap(st["snap"]), t          # incl. float64 angles, bag order
         assert int(state["misc"][0, 3]) == st["draws"], t                   # draws consumed
-        if t + 1 < len(rec["steps"]):                                       # avail-after-step == next mask
+        if t + 1 < len(rec["steps"]) and "restore" not in rec["steps"][t + 1]:  # avail-after-step == next mask
             nxt = rec["steps"][t + 1]["mask"]
             assert [(int(info["available"][0]) >> k) & 1 for k in range(9)] == nxt, t
     env.close()
@@ -176,3 +182,38 @@ def test_host_step_matches_device_step(VTG):
         e2.step_host(host)
         assert torch.equal(o.cpu(), host["obs"]) and torch.equal(r.cpu(), host["reward"])
         assert torch.equal(d.cpu(), host["done"]) and torch.equal(ran.cpu(), host["ran"])
+
+
+def test_init_with_state_batch_matches_c_oracle(VTG):
+    """Batched save/restore: random -99 wildcards over earlier state vectors, then keep playing (Philox mode)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import gen_golden
+    lvt = gen_golden.variant_levels()["twin"]
+    n, seed = 1024, 404
+    env = VTG(n, seed=seed, max_episode_steps=0, auto_reset=False, levels=[product_level(lvt)], render=False)
+    cb = c_oracle.CBatch(c_oracle.CLevel(lvt), n, first_env_id=0, seed=seed)
+    cb.reset()
+    g = torch.Generator().manual_seed(5)
+    rng = np.random.default_rng(6)
+    saved = None
+    for t in range(90):
+        if t % 15 == 14 and saved is not None:
+            vec = saved.copy()
+            keep_pos = rng.random(n) < 0.5
+            wild = rng.random(vec.shape) < 0.4
+            wild[:, :2] = keep_pos[:, None]
+            vec[wild] = -99.0
+            mask = (rng.random(n) < 0.7).astype(np.uint8)
+            env.init_with_state(vec, mask=torch.from_numpy(mask))
+            cb.init_with_state(vec, mask=mask)
+            assert_state_equal(env, cb, "after init_with_state at %d" % t)
+            continue
+        m = torch.from_numpy(cb.mask().astype(np.float32)) + 1e-6
+        a = torch.multinomial(m, 1, generator=g).squeeze(1).to(torch.int32)
+        out = env.step_raw(a.cuda())
+        ref = cb.step(a.numpy())
+        assert_step_equal(out, ref, "step %d" % t)
+        if t % 15 == 7:
+            saved = ref[0].copy()                    # float64 state vectors of an earlier step
+    assert_state_equal(env, cb, "final")

@@ -19,6 +19,11 @@ def test_py_oracle_replays_golden(path):
     assert env.obs() == rec["init"]["obs"]
     for t, st in enumerate(rec["steps"]):
         assert env.mask() == st["mask"], t
+        if "restore" in st:                        # impl:447-481 init_with_state
+            env.init_with_state(list(st["restore"]))
+            assert env.obs() == st["obs"] and env.draws == st["draws"], t
+            assert env.snapshot() == norm_snap(st["snap"]), t
+            continue
         before = env.total_actions
         obs, r, done, _ = env.gym_step(st["a"])
         assert r == st["r"], t
@@ -41,6 +46,11 @@ def test_c_oracle_replays_golden(path):
     assert obs[0].tolist() == rec["init"]["obs"]
     for t, st in enumerate(rec["steps"]):
         assert b.mask()[0].tolist() == st["mask"], t
+        if "restore" in st:
+            b.init_with_state([st["restore"]])
+            assert b.snapshot() == norm_snap(st["snap"]), t
+            assert int(b.state()["misc"][0, 3]) == st["draws"], t
+            continue
         obs, rew, done, ran, ticks = b.step([st["a"]])
         assert bool(ran[0]) == (st["r"] is not None), t
         assert int(rew[0]) == (st["r"] or 0), t

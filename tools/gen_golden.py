@@ -77,19 +77,35 @@ def record(name, level, seed, mode, nsteps):
                        draws_ctor_and_reset=tap.pos,
                        init=dict(snap=rh.impl_snapshot(g.env), obs=obs0),
                        steps=[])
+            saved = []
             for t in range(nsteps):
                 m = g.mask()
                 snap = rh.impl_snapshot(g.env)
+                if mode == "restore" and t % 8 == 7 and saved:
+                    # impl:447-481 init_with_state from an earlier state vector with random -99 wildcards;
+                    # the player position is kept or restored as a pair (a mixed pair can land inside a
+                    # wall, where the reference's option loops never terminate)
+                    vec = list(arng.choice(saved))
+                    keep_pos = arng.random() < 0.5
+                    for i in range(len(vec)):
+                        if (i < 2 and keep_pos) or (i >= 2 and arng.random() < 0.4):
+                            vec[i] = -99
+                    g.env.init_with_state(list(vec))
+                    rec["steps"].append(dict(restore=vec, mask=m, obs=g.env.get_state(), draws=tap.pos,
+                                             snap=rh.impl_snapshot(g.env)))
+                    continue
                 if mode == "solve":
                     a = solver.choose_action(snap, m, kinds=kinds, mirrored=(name.startswith("mirror")),
                                              fallback_rng=arng)
-                elif mode == "runnable":
-                    a = arng.choice([i for i in range(9) if m[i]])
+                elif mode in ("runnable", "restore"):
+                    run = [i for i in range(9) if m[i]]
+                    a = arng.choice(run) if run else arng.randrange(9)
                 else:
                     a = arng.randrange(9)
                 st, r, d, _ = g.step(a)
                 rec["steps"].append(dict(a=a, mask=m, r=r, done=d, obs=st, ticks=g.ticks_last,
                                          draws=tap.pos, snap=rh.impl_snapshot(g.env)))
+                saved.append(st)
                 if d and mode == "solve":
                     break
             rec["tape"] = list(tap.tape)
@@ -109,6 +125,8 @@ def main():
         ("mirror", 5, "solve", 400), ("mirror", 6, "runnable", 150), ("mirror", 8, "random", 150),
         ("altinit", 9, "runnable", 150),
         ("twin", 10, "runnable", 200), ("twin", 12, "runnable", 200), ("twin", 14, "solve", 400),
+        ("default", 31, "restore", 240), ("default", 32, "restore", 240), ("twin", 33, "restore", 240),
+        ("mirror", 34, "restore", 160),
     ]
     for name, seed, mode, n in plan:
         print(record(name, lv[name], seed, mode, n))
