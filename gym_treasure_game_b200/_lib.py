@@ -61,6 +61,7 @@ _SIGNATURES = {
     "tg_render": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "tg_get_state": (C.c_int, [C.c_void_p, C.POINTER(TgStateView), C.c_void_p]),
     "tg_set_state": (C.c_int, [C.c_void_p, C.POINTER(TgStateView), C.c_void_p]),
+    "tg_primitive_step": (C.c_int, [C.c_void_p] * 6),
     "tg_init_with_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tg_set_draw_tape": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tg_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

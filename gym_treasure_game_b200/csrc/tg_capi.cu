@@ -459,6 +459,14 @@ extern "C" int tg_set_state(tg_env *env, const tg_state_view *in, void *stream) 
     return TG_OK;
 }
 
+extern "C" int tg_primitive_step(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done, void *stream) {
+    if (!env || !actions) return fail(TG_ERR_ARG, "null argument");
+    DeviceGuard guard(env->device);
+    CU(launch_primitive(env->B, env->ni, actions, obs, reward, done, (cudaStream_t)stream));
+    env->launches++;
+    return TG_OK;
+}
+
 extern "C" int tg_init_with_state(tg_env *env, const double *states, const uint8_t *mask, void *stream) {
     if (!env || !states) return fail(TG_ERR_ARG, "null argument");
     DeviceGuard guard(env->device);

@@ -19,6 +19,7 @@ struct RenderView {
 cudaError_t launch_step(const BatchView &B, int ni, const int32_t *actions, float *obs, float *reward,
                         uint8_t *done, uint8_t *ran, uint16_t *avail, cudaStream_t s);
 cudaError_t launch_reset(const BatchView &B, int ni, const uint8_t *mask, float *obs, cudaStream_t s);
+cudaError_t launch_primitive(const BatchView &B, int ni, const int32_t *actions, float *obs, float *reward, uint8_t *done, cudaStream_t s);
 cudaError_t launch_init_with_state(const BatchView &B, int ni, const double *states, const uint8_t *mask, cudaStream_t s);
 cudaError_t launch_mask(const BatchView &B, int ni, uint8_t *mask, cudaStream_t s);
 cudaError_t launch_get_state(const BatchView &B, const tg_state_view &v, cudaStream_t s);

@@ -214,6 +214,49 @@ tg_mask_kernel(BatchView B, uint8_t *__restrict__ mask) {
     for (int k = 0; k < TG_NUM_OPTIONS; k++) mask[i * TG_NUM_OPTIONS + k] = (m >> k) & 1u;
 }
 
+// One primitive action per env: _TreasureGameImpl.step(act) (impl:290-359) without the option layer.
+// Action ids are _actions.py:7-13 (anything else falls through every branch like NOP); reward -1, JUMP -5.
+// Episode accounting, done / truncation / auto-reset and statistics behave as in tg_step_kernel.
+template <bool TAPE, int NI>
+__global__ void __launch_bounds__(AUX_THREADS)
+tg_primitive_kernel(BatchView B, const int32_t *__restrict__ actions, float *__restrict__ obs,
+                    float *__restrict__ reward, uint8_t *__restrict__ done_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LevelBlob *levels = reinterpret_cast<LevelBlob *>(smem_raw);
+    __shared__ uint64_t bar;
+    __shared__ int sh_stats[8];
+    if (threadIdx.x < 8) sh_stats[threadIdx.x] = 0;
+    stage_levels(levels, B.levels, B.n_levels, &bar);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (i < B.n) {
+        const LevelBlob &L = levels[B.level_id ? B.level_id[i] : 0];
+        Env<NI> e;
+        uint4 acct;
+        load_env(e, B, i, acct);
+        const int a = actions[i];
+        const uint32_t err0 = e.flags & (1u << F_ERROR);
+        tick<TAPE>(e, L, a);
+        const int r = (a == A_JUMP) ? -5 : -1;                               // impl:15-16,356-359
+        acct.y = (uint32_t)((int)acct.y + r);
+        acct.z += 1u;
+        const bool term = is_done(e, L);
+        const bool trunc = B.max_steps > 0 && acct.z >= (uint32_t)B.max_steps;
+        const int d = (term ? TG_DONE_TERMINATED : 0) | (trunc ? TG_DONE_TRUNCATED : 0);
+        st[ST_TICKS] = 1; st[ST_RAN] = 1; st[ST_STEPS] = 1;
+        st[ST_ERRORS] = ((e.flags & (1u << F_ERROR)) && !err0) ? 1 : 0;
+        if (d) {
+            st[ST_EPISODES] = 1; st[ST_SUCCESS] = term; st[ST_RETURN] = (int)acct.y; st[ST_EPSTEPS] = (int)acct.z;
+            if (B.auto_reset) { reset_env<TAPE>(e, L); acct.y = 0; acct.z = 0; }
+        }
+        store_env(e, B, i, acct);
+        if (obs) write_obs(e, L, obs + i * B.obs_dim, B.obs_dim);
+        if (reward) reward[i] = (float)r;
+        if (done_out) done_out[i] = (uint8_t)d;
+    }
+    stats_accumulate(sh_stats, B.stats, st);
+}
+
 template <bool TAPE, int NI>
 __global__ void __launch_bounds__(AUX_THREADS)
 tg_init_with_state_kernel(BatchView B, const double *__restrict__ states, const uint8_t *__restrict__ mask) {
@@ -357,6 +400,20 @@ cudaError_t launch_reset(const BatchView &B, int ni, const uint8_t *mask, float 
     } else {
         if (tape) tg_reset_kernel<true, 4><<<g, AUX_THREADS, sm, s>>>(B, mask, obs);
         else tg_reset_kernel<false, 4><<<g, AUX_THREADS, sm, s>>>(B, mask, obs);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_primitive(const BatchView &B, int ni, const int32_t *a, float *obs, float *rew, uint8_t *done, cudaStream_t s) {
+    const unsigned g = grid_for(B.n, AUX_THREADS);
+    const size_t sm = level_smem(B);
+    const bool tape = B.tape != nullptr;
+    if (ni <= 2) {
+        if (tape) tg_primitive_kernel<true, 2><<<g, AUX_THREADS, sm, s>>>(B, a, obs, rew, done);
+        else tg_primitive_kernel<false, 2><<<g, AUX_THREADS, sm, s>>>(B, a, obs, rew, done);
+    } else {
+        if (tape) tg_primitive_kernel<true, 4><<<g, AUX_THREADS, sm, s>>>(B, a, obs, rew, done);
+        else tg_primitive_kernel<false, 4><<<g, AUX_THREADS, sm, s>>>(B, a, obs, rew, done);
     }
     return cudaGetLastError();
 }

@@ -163,6 +163,15 @@ class VectorTreasureGame:
                               _ptr(self._ran), None, self._stream()))
         return self._obs, self._reward, self._done, self._ran
 
+    def primitive_step(self, actions: torch.Tensor):
+        """``_TreasureGameImpl.step(action)`` (impl:290-359) for every env: one primitive action
+        (``_actions.py:7-13``), no option layer.  Returns the raw buffers ``(obs, reward, done_bits)``."""
+        if actions.dtype != torch.int32 or actions.device != self.device or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
+        check(self._L.tg_primitive_step(self._h, _ptr(actions), _ptr(self._obs), _ptr(self._reward), _ptr(self._done),
+                                        self._stream()))
+        return self._obs, self._reward, self._done
+
     def make_host_buffers(self):
         """Pinned host buffers for ``step_host`` (actions in; obs, reward, done, ran out)."""
         n = self.num_envs

@@ -162,6 +162,12 @@ int tg_render(tg_env *env, int64_t first, int64_t count, uint8_t *frames, void *
 int tg_get_state(tg_env *env, const tg_state_view *out, void *stream);
 int tg_set_state(tg_env *env, const tg_state_view *in, void *stream);
 
+/* _TreasureGameImpl.step(action) (_treasure_game_impl.py:290-359): one primitive action per env, no option layer.
+ * actions DEV [N] int32 in _actions.py:7-13 (0 NOP, 1 UP, 2 DOWN, 3 LEFT, 4 RIGHT, 5 JUMP, 6 INTERACT; other ids act
+ * as NOP like the reference's if-chain); reward -1, JUMP -5; obs / done / accounting / auto-reset as in tg_step. */
+enum { TG_ACT_NOP = 0, TG_ACT_UP, TG_ACT_DOWN, TG_ACT_LEFT, TG_ACT_RIGHT, TG_ACT_JUMP, TG_ACT_INTERACT };
+int tg_primitive_step(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done, void *stream);
+
 /* _TreasureGameImpl.init_with_state (_treasure_game_impl.py:447-481), quirks included: states DEV [N][obs_dim]
  * float64 normalised state vectors in get_state_descriptors order (:380-400), -99 = keep the current value;
  * every key / gold / bolt reads the first slot of its name; facing is forced right; the bag, the jump ticker and

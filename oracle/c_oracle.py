@@ -48,6 +48,7 @@ def lib():
         L.tgo_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.tgo_batch_init_with_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.tgo_batch_get_pt.argtypes = [C.c_void_p, C.c_void_p]
+        L.tgo_batch_prim_step.argtypes = [C.c_void_p] * 5
         _lib = L
     return _lib
 
@@ -128,6 +129,14 @@ class CBatch:
     def step_fast(self, actions, rew, done):
         """No per-call allocations (for timing)."""
         lib().tgo_batch_step(self.h, _p(actions), None, _p(rew), _p(done), None, None)
+
+    def prim_step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        obs = np.zeros((self.n, self.level.obs_dim), dtype=np.float64)
+        rew = np.zeros(self.n, dtype=np.float32)
+        done = np.zeros(self.n, dtype=np.uint8)
+        lib().tgo_batch_prim_step(self.h, _p(a), _p(obs), _p(rew), _p(done))
+        return obs, rew, done
 
     def init_with_state(self, states, mask=None):
         st = np.ascontiguousarray(states, dtype=np.float64).reshape(self.n, self.level.obs_dim)

@@ -598,6 +598,27 @@ void tgo_batch_step(void *bp, const int32_t *actions, double *obs, float *reward
     b->stats[4] += s4; b->stats[5] += s5; b->stats[6] += b->n; b->stats[7] += s7;
 }
 
+/* one primitive action per env (impl:290-359), same accounting as tgo_batch_step */
+void tgo_batch_prim_step(void *bp, const int32_t *actions, double *obs, float *reward, uint8_t *done)
+{
+    batch_t *b = bp; int od = b->lv->obs_dim;
+    for (int64_t i = 0; i < b->n; i++) {
+        env_t *e = &b->e[i];
+        int err0 = e->error;
+        int r = tick(b, e, actions[i]);
+        e->ep_return += r; e->ep_steps += 1;
+        int term = is_done(e);
+        int trunc = (b->max_steps > 0 && e->ep_steps >= b->max_steps);
+        int d = term | (trunc << 1);
+        b->stats[4] += 1; b->stats[5] += 1; b->stats[6] += 1; b->stats[7] += (e->error && !err0);
+        if (d) { b->stats[0] += 1; b->stats[1] += term; b->stats[2] += e->ep_return; b->stats[3] += e->ep_steps; }
+        if (d && b->auto_reset) env_reset(b, e);
+        if (obs) write_obs(e, obs + i * od);
+        if (reward) reward[i] = (float)r;
+        if (done) done[i] = (uint8_t)d;
+    }
+}
+
 void tgo_batch_init_with_state(void *bp, const double *states, const uint8_t *mask)
 {
     batch_t *b = bp; int od = b->lv->obs_dim;

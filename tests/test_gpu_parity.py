@@ -217,3 +217,24 @@ def test_init_with_state_batch_matches_c_oracle(VTG):
         if t % 15 == 7:
             saved = ref[0].copy()                    # float64 state vectors of an earlier step
     assert_state_equal(env, cb, "final")
+
+
+def test_primitive_step_matches_c_oracle(VTG):
+    """tg_primitive_step: one raw action per env (impl:290-359), no option layer."""
+    lvt = po.default_level()
+    n, seed = 2048, 909
+    env = VTG(n, seed=seed, max_episode_steps=400, auto_reset=True, render=False)
+    cb = c_oracle.CBatch(c_oracle.CLevel(lvt), n, first_env_id=0, seed=seed, max_episode_steps=400, auto_reset=True)
+    cb.reset()
+    g = torch.Generator().manual_seed(12)
+    weights = torch.tensor([1.0, 2, 3, 4, 4, 1, 1, 0.2])          # id 7 is not an action: falls through like NOP
+    for t in range(900):
+        a = torch.multinomial(weights.expand(n, -1), 1, generator=g).squeeze(1).to(torch.int32)
+        obs, rew, done = env.primitive_step(a.cuda())
+        o2, r2, d2 = cb.prim_step(a.numpy())
+        np.testing.assert_array_equal(rew.cpu().numpy(), r2, err_msg=str(t))
+        np.testing.assert_array_equal(done.cpu().numpy(), d2, err_msg=str(t))
+        np.testing.assert_array_equal(obs.cpu().numpy(), o2.astype(np.float32), err_msg=str(t))
+        if t % 150 == 149:
+            assert_state_equal(env, cb, "tick %d" % t)
+    assert list(env.stats().values()) == cb.stats().tolist()

@@ -91,3 +91,33 @@ def test_appendix_e_known_answer():
     pe.reset()
     tot2 = sum(pe.gym_step(a)[1] for a in acts)
     assert (tot2, pe.is_done(), pe.px, pe.py, pe.total_actions, pe.draws) == (-1836, True, 216, 1, 1792, 1570)
+
+
+def test_primitive_step_live():
+    """_TreasureGameImpl.step(act) (impl:290-359) with raw actions, reference vs both oracles."""
+    lvt = po.default_level()
+    clv = c_oracle.CLevel(lvt)
+    for seed in range(4):
+        random.seed(seed)
+        arng = random.Random(seed + 50)
+        with rh.DrawTap() as tap:
+            g = rh.RefGame()
+            g.reset()
+            pe = po.OracleEnv(lvt, po.TapeUniform(tap.tape))
+            pe.reset()
+            acts, snaps = [], []
+            for t in range(1500):
+                a = arng.choice([0, 1, 2, 3, 3, 3, 4, 4, 4, 5, 6, 7])      # 7: not an action id (falls through like NOP)
+                r = g.env.step(a)
+                assert pe.tick(a) == r
+                assert pe.snapshot() == rh.impl_snapshot(g.env)
+                acts.append(a)
+                snaps.append((rh.impl_snapshot(g.env), g.env.get_state(), r))
+            tape = list(tap.tape)
+        cb = c_oracle.CBatch(clv, 1)
+        cb.set_tape([tape])
+        cb.reset()
+        cb.reset()
+        for a, (snap, st, r) in zip(acts, snaps):
+            obs, rew, _ = cb.prim_step([a])
+            assert cb.snapshot() == snap and obs[0].tolist() == st and int(rew[0]) == r
