@@ -40,7 +40,7 @@ WORKLOAD = ("treasure_game-v0 vector-state obs, 1,048,576 envs per GPU (BASELINE
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.2):
+    def __init__(self, index, period=0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -319,11 +319,12 @@ def main():
                    "actions": "torch.randint on the device before every step, outside the timed event pair", "collective": "NCCL all-reduce of int64[8] stats every 100 steps, side stream"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                "api": "tg_step_host (pinned host buffers; copies + stream sync inside the call)"},
+                "api": "tg_step_host (pinned host buffers; H2D actions, chunked step kernels overlapping the D2H of obs/reward/done/ran, stream sync inside the call)"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": (n * ALGO_BYTES_PER_ENV_STEP) / (total_s / K) / 1e9,
                      "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
-                     "kernel": "tg_step_kernel<false,2>", "algorithmic_bytes_per_launch": n * ALGO_BYTES_PER_ENV_STEP},
+                     "kernel": "tg_step_kernel<false,2,2048>", "algorithmic_bytes_per_launch": n * ALGO_BYTES_PER_ENV_STEP,
+                     "note": "instruction-issue / serial-chain bound, not HBM bound (DESIGN.md 3.1); see work.primitive_ticks_per_s"},
         "work": {"runnable_fraction": stats["runnable_steps"] / max(stats["gym_steps"], 1),
                  "primitive_ticks_per_step": stats["primitive_ticks"] / max(stats["gym_steps"], 1),
                  "primitive_ticks_per_s": stats["primitive_ticks"] / total_s if stats["gym_steps"] else None,
@@ -409,7 +410,7 @@ def aux_configs(torch, dev, peak):
     out["cfg4_render_16384_envs"] = {
         "frames_per_s_render_only": n / t_r, "frames_per_s_step_plus_render": n / t_sr, "ms_render": t_r * 1e3,
         "roofline": {"bound": "hbm", "achieved": n * ALGO_BYTES_PER_FRAME / t_r / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": n * ALGO_BYTES_PER_FRAME / t_r / 1e9 / peak, "kernel": "tg_render_kernel",
+                     "frac": n * ALGO_BYTES_PER_FRAME / t_r / 1e9 / peak, "kernel": "tg_render_stream_kernel",
                      "note": "20.6 GB written per launch (> L2)"}}
     env.close()
     return out

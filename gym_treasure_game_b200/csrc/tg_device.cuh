@@ -103,8 +103,11 @@ __device__ __forceinline__ double handle_angle(bool up, double u) {
 // tiles
 // ---------------------------------------------------------------------------
 // pixel -> padded cell index floor(v/48)+PAD.  No clamps: px in [0, W) and py in [-S, H) are invariants of
-// the dynamics (tg_set_state clamps injected positions), so every probe lands inside the 32x32 table.
-__device__ __forceinline__ int pad_cell(int v) { return (int)((unsigned)(v + PAD * S) / (unsigned)S); }
+// the dynamics (tg_set_state / tg_init_with_state clamp injected positions), so every probe lands inside the
+// 32x32 table.  t/48 == (t*1366)>>16 exactly for 0 <= t < 1536 = 32*48 (1366/65536 exceeds 1/48 by 1.0e-5,
+// which adds < 0.016 to the quotient; the largest fractional part is 47/48 = 0.979), one IMAD + one shift.
+static_assert(S == 48 && TSTRIDE == 32, "pad_cell's multiply-shift division is derived for 48-px cells and a 32-cell table");
+__device__ __forceinline__ int pad_cell(int v) { return (int)(((unsigned)(v + PAD * S) * 1366u) >> 16); }
 __device__ __forceinline__ int pad_idx(int c) { return min(max(c + PAD, 0), TSTRIDE - 1); }
 
 // effective type of the cell with padded indices (ixp, iyp)    impl:218-225 + objs:246-253
