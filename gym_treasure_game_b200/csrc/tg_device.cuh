@@ -32,7 +32,7 @@ struct Env {
     // row-mask cache for the two probes every tick makes (valid while playery == m_py and the doors
     // do not move): m_fall = non-open cells of the rows of y and y+50, m_side = solid cells of the
     // rows of y+4 and y+44; bit = padded column.  A walk never changes y, so its ticks only shift/test.
-    int m_py;
+    int m_py, m_py_side;         // playery each mask was built for (INT_MIN = empty)
     uint32_t m_fall, m_side;
     // where this env's handle angles live (touched only by interact / reset / obs)
     double *angles;              // angles[h * n] is handle h
@@ -169,22 +169,29 @@ __device__ __forceinline__ uint32_t door_bits(const LevelBlob &L, uint32_t flags
     return li ? L.door_lut[li - 1][closed] : 0u;
 }
 template <int NI>
-__device__ __forceinline__ void row_cache_fill(Env<NI> &e, const LevelBlob &L) {
-    const int r0 = pad_cell(e.py), r1 = pad_cell(e.py + 50), r2 = pad_cell(e.py + 4), r3 = pad_cell(e.py + 44);
+__device__ __forceinline__ void fall_cache_fill(Env<NI> &e, const LevelBlob &L) {
+    const int r0 = pad_cell(e.py), r1 = pad_cell(e.py + 50);
     e.m_fall = L.row_nonopen[r0] | door_bits(L, e.flags, r0) | L.row_nonopen[r1] | door_bits(L, e.flags, r1);
-    e.m_side = L.row_solid[r2] | door_bits(L, e.flags, r2) | L.row_solid[r3] | door_bits(L, e.flags, r3);
     e.m_py = e.py;
 }
+template <int NI>
+__device__ __forceinline__ void side_cache_fill(Env<NI> &e, const LevelBlob &L) {
+    const int r2 = pad_cell(e.py + 4), r3 = pad_cell(e.py + 44);
+    e.m_side = L.row_solid[r2] | door_bits(L, e.flags, r2) | L.row_solid[r3] | door_bits(L, e.flags, r3);
+    e.m_py_side = e.py;
+}
+template <int NI>
+__device__ __forceinline__ void row_cache_drop(Env<NI> &e) { e.m_py = INT_MIN; e.m_py_side = INT_MIN; }
 // impl:283-288 through the cache
 template <int NI>
 __device__ __forceinline__ bool can_fall_m(Env<NI> &e, const LevelBlob &L) {
-    if (e.m_py != e.py) row_cache_fill(e, L);
+    if (e.m_py != e.py) fall_cache_fill(e, L);
     return (((e.m_fall >> pad_cell(e.px - 10)) | (e.m_fall >> pad_cell(e.px + 10))) & 1u) == 0u;
 }
 // impl:259-281 through the cache (x = playerx -+ 16)
 template <int NI>
 __device__ __forceinline__ bool side_free_m(Env<NI> &e, const LevelBlob &L, int x) {
-    if (e.m_py != e.py) row_cache_fill(e, L);
+    if (e.m_py_side != e.py) side_cache_fill(e, L);
     return ((e.m_side >> pad_cell(x)) & 1u) == 0u;
 }
 // impl:240-257 in mask form: up: y > 1 and LADDER in rows of y-4, y, y+44; down: rows of y, next, y+51; columns of x-+12
@@ -320,8 +327,29 @@ __device__ __forceinline__ int noisy_from_k(uint64_t k, bool negative) {
 template <bool TAPE, int NI>
 __device__ __forceinline__ int noisy(Env<NI> &e, bool negative) { return noisy_from_k(draw_k<TAPE>(e), negative); }
 
+// impl:350-354: key / gold within 24 px of (playerx, playery + 24) go to the next bag cell, item (= file) order
+template <int NI>
+__device__ __forceinline__ void pickups(Env<NI> &e, const LevelBlob &L) {
+    const int bx = (L.cw - 1) * S, by = (L.ch - 1) * S;
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+        if (i < L.n_items && near_px(e.px, e.py, e.ix[i], e.iy[i], 24 * 24)) {
+            const int len = bag_len(e.flags);
+            e.ix[i] = bx - len * S; e.iy[i] = by;                                    // objs:34-38
+            if (len < TG_MAX_ITEMS) {                                                // player_bag.append(obj)
+                e.flags = (e.flags & ~(3u << (F_BAGORD + 2 * len))) | ((uint32_t)i << (F_BAGORD + 2 * len));
+                e.flags = (e.flags & ~(7u << F_BAGLEN)) | ((uint32_t)(len + 1) << F_BAGLEN);
+            } else {
+                e.flags |= 1u << F_ERROR;     // a fifth bag entry (only reachable through repeated re-pickups) is not representable
+            }
+        }
+    }
+}
+
+// `ladder_ok` >= 0 passes the ladder probe the option policy has just evaluated for UP / DOWN (same state, same
+// result as impl:298 / :302 would compute again); -1 = evaluate here.
 template <bool TAPE, int NI>
-__device__ __forceinline__ void tick(Env<NI> &e, const LevelBlob &L, int act) {
+__device__ __forceinline__ void tick(Env<NI> &e, const LevelBlob &L, int act, int ladder_ok = -1) {
     int xd = 0, yd = 0;
     e.total_actions++;
     if (act >= A_UP && act <= A_RIGHT) {
@@ -329,7 +357,8 @@ __device__ __forceinline__ void tick(Env<NI> &e, const LevelBlob &L, int act) {
         // the move is permitted by the ladder probe (UP/DOWN) or the side probe (LEFT/RIGHT), then
         // noisy() draws once; LEFT/RIGHT also set facing_right (unchanged when blocked).
         const bool horiz = act >= A_LEFT, neg = (act == A_UP) || (act == A_LEFT);
-        const bool ok = horiz ? side_free_m(e, L, e.px + (neg ? -16 : 16)) : ladder_probe(L, e.px, e.py, neg);
+        const bool ok = horiz ? side_free_m(e, L, e.px + (neg ? -16 : 16))
+                              : (ladder_ok >= 0 ? ladder_ok != 0 : ladder_probe(L, e.px, e.py, neg));
         if (ok) {
             const int d = noisy<TAPE>(e, neg);
             if (horiz) { xd = d; e.flags = (e.flags & ~(1u << F_FACING)) | (neg ? 0u : (1u << F_FACING)); }
@@ -340,7 +369,7 @@ __device__ __forceinline__ void tick(Env<NI> &e, const LevelBlob &L, int act) {
             e.flags = set_ticker(e.flags, draw_k<TAPE>(e) > (1ull << 51) ? 23 : 22);   // impl:316-319: random() > 0.25
     } else if (act == A_INTERACT) {
         interact<TAPE>(e, L);
-        e.m_py = INT_MIN;            // doors may have moved: drop the row-mask cache
+        row_cache_drop(e);           // doors may have moved
     }
     int tk = ticker(e.flags);
     if (tk > 0) {                                                                    // impl:331-334
@@ -358,21 +387,7 @@ __device__ __forceinline__ void tick(Env<NI> &e, const LevelBlob &L, int act) {
     } else {
         e.py += yd;                                                                  // impl:348
     }
-    // impl:350-354 pickups, item (= file) order
-    const int bx = (L.cw - 1) * S, by = (L.ch - 1) * S;
-#pragma unroll
-    for (int i = 0; i < NI; i++) {
-        if (i < L.n_items && near_px(e.px, e.py, e.ix[i], e.iy[i], 24 * 24)) {
-            const int len = bag_len(e.flags);
-            e.ix[i] = bx - len * S; e.iy[i] = by;                                    // objs:34-38
-            if (len < TG_MAX_ITEMS) {                                                // player_bag.append(obj)
-                e.flags = (e.flags & ~(3u << (F_BAGORD + 2 * len))) | ((uint32_t)i << (F_BAGORD + 2 * len));
-                e.flags = (e.flags & ~(7u << F_BAGLEN)) | ((uint32_t)(len + 1) << F_BAGLEN);
-            } else {
-                e.flags |= 1u << F_ERROR;     // a fifth bag entry (only reachable through repeated re-pickups) is not representable
-            }
-        }
-    }
+    pickups(e, L);
 }
 
 // ---------------------------------------------------------------------------
@@ -487,15 +502,38 @@ __device__ __forceinline__ int run_option_to_end(Env<NI> &e, const LevelBlob &L,
     const int s = (k == TG_GO_LEFT || k == TG_DOWN_LEFT || k == TG_JUMP_LEFT) ? -1 : 1;
     int n = 0;
     bool done = false;
+    if (k <= TG_GO_RIGHT) {
+        // Straight-line form of the go_left / go_right tick for the common situation: no jump in progress
+        // and ground under the feet.  Then tick(LEFT/RIGHT) (impl:290-359) reduces to: count the action, move
+        // by noisy() if the side probe is free (and face that way), pick up.  playery never changes, so the
+        // two row masks are loop constants.  Any other situation (ticker > 0, can_fall) leaves the loop
+        // *before* the tick is executed and the general loop below takes over from the same state.
+        if (e.m_py != e.py) fall_cache_fill(e, L);
+        if (e.m_py_side != e.py) side_cache_fill(e, L);
+        const uint32_t mside = e.m_side, mfall = e.m_fall;
+        while (!done && ticker(e.flags) == 0 &&
+               (((mfall >> pad_cell(e.px - 10)) | (mfall >> pad_cell(e.px + 10))) & 1u) != 0u) {
+            done = abs(tpx - e.px) < 4;                   // opts:80-85: the action of the final policy step still runs
+            e.total_actions++;
+            if (((mside >> pad_cell(e.px + 16 * s)) & 1u) == 0u) {
+                e.px += noisy<TAPE>(e, s < 0);
+                e.flags = (e.flags & ~(1u << F_FACING)) | (s < 0 ? 0u : (1u << F_FACING));
+            }
+            pickups(e, L);
+            n++;
+            if (n >= TG_TICK_CAP && !done) { e.flags |= 1u << F_ERROR; return n; }
+        }
+        if (done) return n;
+    }
     do {
-        int act;
+        int act, lad = -1;
         const bool al = abs(tpx - e.px) < 4;              // close_enough_*  (opts:69-72 ...)
         if (k <= TG_GO_RIGHT) {                           // opts:74-85 / 146-157
             done = al; act = (s < 0) ? A_LEFT : A_RIGHT;
         } else if (k == TG_UP_LADDER) {                   // opts:168-173
-            done = !ladder_probe(L, e.px, e.py, true); act = done ? A_NOP : A_UP;
+            done = !ladder_probe(L, e.px, e.py, true); act = done ? A_NOP : A_UP; lad = 1;
         } else if (k == TG_DOWN_LADDER) {                 // opts:184-189
-            done = !ladder_probe(L, e.px, e.py, false); act = done ? A_NOP : A_DOWN;
+            done = !ladder_probe(L, e.px, e.py, false); act = done ? A_NOP : A_DOWN; lad = 1;
         } else if (k == TG_INTERACT) {                    // opts:457-460
             done = true; act = A_INTERACT;
         } else if (k <= TG_DOWN_RIGHT) {                  // opts:231-244 / 426-439
@@ -511,7 +549,7 @@ __device__ __forceinline__ int run_option_to_end(Env<NI> &e, const LevelBlob &L,
                 act = ((s < 0) != rev) ? A_LEFT : A_RIGHT;
             }
         }
-        tick<TAPE>(e, L, act);
+        tick<TAPE>(e, L, act, lad);
         n++;
         if (n >= TG_TICK_CAP && !done) { e.flags |= 1u << F_ERROR; break; }
     } while (!done);
@@ -672,7 +710,7 @@ __device__ void init_with_state_env(Env<NI> &e, const LevelBlob &L, const double
             set_val<TAPE>(e, L, o, st[first_bolt] > 0.5);
         }
     }
-    e.m_py = INT_MIN;
+    row_cache_drop(e);
 }
 
 // ---------------------------------------------------------------------------
@@ -690,8 +728,7 @@ __device__ __forceinline__ int hi16(uint32_t v) { return (int)(int16_t)(v >> 16)
 
 // position / flags / items only (enough for can_run and the option targets)
 template <int NI>
-__device__ __forceinline__ void load_core(Env<NI> &e, const BatchView &B, int64_t i) {
-    uint4 c = B.core[i];
+__device__ __forceinline__ void load_core(Env<NI> &e, const BatchView &B, int64_t i, uint4 c) {
     e.px = core_px(c.x); e.py = hi16(c.x); e.sticky = core_sticky(c.x); e.flags = c.y;
     e.ix[0] = lo16(c.z); e.iy[0] = hi16(c.z);
     if (NI > 1) { e.ix[1] = lo16(c.w); e.iy[1] = hi16(c.w); }
@@ -701,6 +738,9 @@ __device__ __forceinline__ void load_core(Env<NI> &e, const BatchView &B, int64_
         if (NI > 3) { e.ix[3] = lo16(h.y); e.iy[3] = hi16(h.y); }
     }
 }
+
+template <int NI>
+__device__ __forceinline__ void load_core(Env<NI> &e, const BatchView &B, int64_t i) { load_core(e, B, i, B.core[i]); }
 
 template <int NI>
 __device__ __forceinline__ void load_env(Env<NI> &e, const BatchView &B, int64_t i, uint4 &acct) {
@@ -715,7 +755,7 @@ __device__ __forceinline__ void load_env(Env<NI> &e, const BatchView &B, int64_t
         if (NI > 3) { e.ix[3] = lo16(h.y); e.iy[3] = hi16(h.y); }
     }
     e.draws = acct.x; e.total_actions = acct.w;
-    e.m_py = INT_MIN; e.m_fall = 0; e.m_side = 0;
+    row_cache_drop(e); e.m_fall = 0; e.m_side = 0;
     e.blk = 0xFFFFFFFFu; e.w0 = e.w1 = e.w2 = e.w3 = 0;
     e.key0 = B.seed_lo; e.key1 = B.seed_hi;
     uint64_t id = (uint64_t)(B.first_env_id + i);
