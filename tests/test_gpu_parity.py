@@ -57,7 +57,7 @@ def test_cuda_replays_reference_golden(VTG, path):
 
 
 @pytest.mark.parametrize("name,n,steps,max_steps", [("default", 4096, 250, 100), ("twin", 2048, 250, 60),
-                                                    ("mirror", 1024, 150, 0)])
+                                                    ("mirror", 1024, 150, 0), ("wide", 1536, 200, 40)])
 def test_cuda_matches_c_oracle_philox(VTG, name, n, steps, max_steps):
     """BASELINE config 2 shape: batched envs, uniform-random actions, time-limit auto-reset."""
     import sys, os

@@ -91,3 +91,28 @@ def test_mixed_level_batch_frames():
     for i in range(0, n, 7):
         want = ro.render_frame(lvts[ids[i]], refs[ids[i]].snapshot(i), bgs[ids[i]])
         assert np.array_equal(frames[i], want), i
+
+
+def test_other_grid_size_frames():
+    """An 18 x 7 layout (864 x 336 frames): unit rows, job grid and tile layer all follow the level."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import gen_golden
+    from gym_treasure_game_b200 import VectorTreasureGame
+    lvt = gen_golden.variant_levels()["wide"]
+    n, seed = 200, 23
+    env = VectorTreasureGame(n, seed=seed, auto_reset=False, levels=[product_level(lvt)])
+    cb = c_oracle.CBatch(c_oracle.CLevel(lvt), n, first_env_id=0, seed=seed)
+    cb.reset()
+    bg = ro.background(lvt.tiles)
+    g = torch.Generator().manual_seed(2)
+    for t in range(45):
+        m = torch.from_numpy(cb.mask().astype(np.float32)) + 1e-6
+        a = torch.multinomial(m, 1, generator=g).squeeze(1).to(torch.int32)
+        env.step_raw(a.cuda())
+        cb.step(a.numpy())
+    frames = env.render().cpu().numpy()
+    assert frames.shape == (n, 336, 864, 3)
+    for i in range(0, n, 9):
+        want = ro.render_frame(lvt, cb.snapshot(i), bg)
+        assert np.array_equal(frames[i], want), (i, int((frames[i] != want).sum()))

@@ -53,6 +53,19 @@ def variant_levels():
         (po.K_BOLT, 1, False, po.K_HANDLE, 2, True),
     ]
     lv["twin"] = twin
+    # a different grid size (18 x 7): exercises the data-driven level path end to end
+    wide = po.LevelText.from_strings(
+        "\n".join([
+            "//////////////L///",
+            "/                /",
+            "////L/////////////",
+            "/                /",
+            "//////L//  ///////",
+            "/                /",
+            "//////////////////"]) + "\n",
+        "handle 15 1 True\ndoor 8 1 True\nkey 12 3\nbolt 2 5 True\ndoor 12 5 True\ngold 15 5\n",
+        "handle 0 True door 0 True\nhandle 0 False door 0 False\nbolt 0 True door 1 True\nbolt 0 False door 1 False\n")
+    lv["wide"] = wide
     return lv
 
 
@@ -127,6 +140,7 @@ def main():
         ("twin", 10, "runnable", 200), ("twin", 12, "runnable", 200), ("twin", 14, "solve", 400),
         ("default", 31, "restore", 240), ("default", 32, "restore", 240), ("twin", 33, "restore", 240),
         ("mirror", 34, "restore", 160),
+        ("wide", 41, "runnable", 300), ("wide", 42, "random", 200), ("wide", 43, "restore", 200),
     ]
     for name, seed, mode, n in plan:
         print(record(name, lv[name], seed, mode, n))
