@@ -324,6 +324,7 @@ extern "C" int tg_create(const tg_level *const *levels, int32_t n_levels, const 
             CUE(cudaMemcpy(sp, levels[l]->sprites.data(), levels[l]->sprites.size() * 4, cudaMemcpyHostToDevice));
             R.assets[l].background = bg; R.assets[l].sprites = sp;
         }
+        CUE(dev_alloc(e, &R.job_counter, (size_t)1));
         e->has_render = true;
     }
     // constructor draws + initial state (impl:31-53)

@@ -14,6 +14,7 @@ struct RenderAssets {
 struct RenderView {
     RenderAssets assets[TG_MAX_LEVELS];
     int32_t frame_w, frame_h, cw, ch;
+    unsigned long long *job_counter;   // device word used by the streaming renderer to hand out jobs
 };
 
 cudaError_t launch_step(const BatchView &B, int ni, const int32_t *actions, float *obs, float *reward,

@@ -210,7 +210,7 @@ tg_render_band_kernel(BatchView B, RenderView R, int64_t first, uint8_t *__restr
 // ===========================================================================
 constexpr int RS_THREADS = 256;
 constexpr int RS_PATCH_THREADS = RS_THREADS - 32;     // warps 1..7 compose dirty units; warp 0 streams clean ones
-constexpr int RS_EB = 64;
+constexpr int RS_EB_MAX = 256;        // envs per job: array bound; the launcher picks eb <= RS_EB_MAX
 
 __device__ __forceinline__ void patch_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(RS_PATCH_THREADS) : "memory"); }
 
@@ -370,19 +370,20 @@ __device__ __forceinline__ void tma_store(void *dst, uint32_t src_a, uint32_t by
 //   mode 2: prefix state differs from K*  -> W = pristine rows re-fetched by TMA (L2) + every object
 // Drawing order is preserved: everything outside the prefix comes later in file order, the hero last.
 __global__ void __launch_bounds__(RS_THREADS)
-tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int64_t first, int64_t count,
-                        uint8_t *__restrict__ frames, int dbg) {
+tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int EB, int64_t first, int64_t count,
+                        uint8_t *__restrict__ frames, unsigned long long *__restrict__ job_counter, int dbg) {
     extern __shared__ __align__(128) uint8_t rs_smem[];
     __shared__ uint64_t bar, bar2;
-    __shared__ uint4 s_core[RS_EB];
-    __shared__ uint2 s_items23[RS_EB];
-    __shared__ short2 s_lever[RS_EB][TG_MAX_HANDLES];
+    __shared__ uint4 s_core[RS_EB_MAX];
+    __shared__ uint2 s_items23[RS_EB_MAX];
+    __shared__ short2 s_lever[RS_EB_MAX][TG_MAX_HANDLES];
     __shared__ int8_t disc_lo[32], disc_hi[32];
     __shared__ short4 s_obj[TG_MAX_OBJECTS];          // draw list: x = ox, y = oy, z = kind, w = index in kind
     __shared__ short2 s_item_init[TG_MAX_ITEMS];      // initial pixel position of every key / gold
     __shared__ int s_nobj, s_nhandles, s_nitems, s_votes;
-    __shared__ uint16_t s_key[RS_EB];
-    __shared__ uint8_t s_mode[RS_EB];
+    __shared__ uint16_t s_key[RS_EB_MAX];
+    __shared__ uint8_t s_mode[RS_EB_MAX];
+    __shared__ long long s_job;
     const int tid = threadIdx.x;
     const uint32_t unit_bytes = (uint32_t)(UR * W * 3);
     uint8_t *C = rs_smem, *W0 = rs_smem + unit_bytes, *W1 = rs_smem + 2 * (size_t)unit_bytes;
@@ -424,16 +425,22 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int64
     __syncthreads();
 
     const int ntypes = H / UR;
-    const int nblocks = (int)((count + RS_EB - 1) / RS_EB);
+    const int nblocks = (int)((count + EB - 1) / EB);
     const int64_t njobs = (int64_t)ntypes * nblocks;
     const int nobj = s_nobj;
     uint32_t parity = 0, parity2 = 0;
     int G = 0, lastW[2] = {-1, -1}, nd = 0;          // bulk-group bookkeeping of the composer's issuer (tid 32)
 
-    for (int64_t job = blockIdx.x; job < njobs; job += gridDim.x) {
+    for (;;) {
+        // jobs are handed out dynamically (lever rows cost more than plain rows); the previous job's final
+        // __syncthreads() guarantees nobody still reads s_job
+        if (tid == 0) s_job = (long long)atomicAdd(job_counter, 1ull);
+        __syncthreads();
+        const int64_t job = s_job;
+        if (job >= njobs) break;
         const int t = (int)(job / nblocks), blk = (int)(job % nblocks);
-        const int64_t e0 = (int64_t)blk * RS_EB;
-        const int ne = (int)min((int64_t)RS_EB, count - e0);
+        const int64_t e0 = (int64_t)blk * EB;
+        const int ne = (int)min((int64_t)EB, count - e0);
         const int y0 = t * UR;
         const uint8_t *pristine = A.background + (size_t)y0 * W * 3;
         auto rows_hit = [&](int oy, int above, int below) { return oy + S + below > y0 && oy - above < y0 + UR; };
@@ -619,7 +626,7 @@ cudaError_t render_configure() {
     if (g_render_configured) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(tg_render_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tg_render_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    e = cudaFuncSetAttribute(tg_render_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) return e;
     int dev = 0;
     e = cudaGetDevice(&dev);
@@ -629,14 +636,15 @@ cudaError_t render_configure() {
     return e;
 }
 
-// rows per unit of the streaming renderer: the largest divisor of 48 whose three buffers fit three times per
-// SM (measured on B200, 16384 frames of 672x624, final kernel: UR 6/8/12/16/24 -> 4.84/5.00/5.19/5.08/4.09 TB/s)
+// rows per unit of the streaming renderer: the largest divisor of 48 whose three buffers fit twice per SM.
+// Measured on B200 (final kernel, dynamic jobs, 16384 frames of 672x624, 256 envs per job):
+// UR 8/12/16/24 -> 5.07/5.04/5.61/4.46 TB/s.
 static int pick_unit_rows(int W) {
     static int forced = -1;
     if (forced < 0) { const char *v = getenv("TG_RENDER_UR"); forced = v ? atoi(v) : 0; }
     if (forced > 0 && 48 % forced == 0) return forced;
     static const int cand[] = {48, 24, 16, 12, 8, 6, 4};
-    for (int ur : cand) if ((size_t)3 * ur * W * 3 <= 74 * 1024) return ur;
+    for (int ur : cand) if ((size_t)3 * ur * W * 3 <= 100 * 1024) return ur;
     return 4;
 }
 
@@ -653,11 +661,23 @@ cudaError_t launch_render(const BatchView &B, const RenderView &R, int64_t first
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tg_render_stream_kernel, RS_THREADS, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
-        const int64_t njobs = (int64_t)(R.frame_h / ur) * ((count + RS_EB - 1) / RS_EB);
-        const int64_t grid = njobs < (int64_t)g_num_sms * per_sm ? njobs : (int64_t)g_num_sms * per_sm;
+        // envs per job: as many as possible (the per-job set-up -- pristine rows, vote, baking -- is amortised
+        // over them: 16384 frames, 32/64/128/256 envs -> 5.27/5.38/5.49/5.61 TB/s) while leaving >= 8 jobs per
+        // resident CTA so that the dynamic job queue still balances (4096 frames: 256 -> 4.3, 64 -> 5.45 TB/s)
+        static int eb_forced = -1;
+        if (eb_forced < 0) { const char *v = getenv("TG_RENDER_EB"); eb_forced = v ? atoi(v) : 0; }
+        const int64_t slots = (int64_t)g_num_sms * per_sm;
+        int eb = RS_EB_MAX;
+        while (eb > 16 && (int64_t)(R.frame_h / ur) * ((count + eb - 1) / eb) < 8 * slots) eb >>= 1;
+        if (eb_forced >= 16 && eb_forced <= RS_EB_MAX) eb = eb_forced;
+        const int64_t njobs = (int64_t)(R.frame_h / ur) * ((count + eb - 1) / eb);
+        const int64_t grid = njobs < slots ? njobs : slots;
         static int dbg = -1;
         if (dbg < 0) { const char *v = getenv("TG_RENDER_DBG"); dbg = v ? atoi(v) : 0; }
-        tg_render_stream_kernel<<<(unsigned)grid, RS_THREADS, smem, s>>>(B, R.assets[0], R.frame_w, R.frame_h, ur, first, count, frames, dbg);
+        e = cudaMemsetAsync(R.job_counter, 0, sizeof(unsigned long long), s);
+        if (e != cudaSuccess) return e;
+        tg_render_stream_kernel<<<(unsigned)grid, RS_THREADS, smem, s>>>(B, R.assets[0], R.frame_w, R.frame_h, ur, eb, first, count,
+                                                                         frames, R.job_counter, dbg);
         return cudaGetLastError();
     }
     const size_t band_bytes = (size_t)S * R.frame_w * 3;
