@@ -35,7 +35,7 @@ NOP, UP, DOWN, LEFT, RIGHT, JUMP, INTERACT = range(7)   # _actions.py:7-13
 JUMP_REWARD, STEP_REWARD = -5, -1                   # impl:15-16
 OPTION_NAMES = ["go_left", "go_right", "up_ladder", "down_ladder", "interact",
                 "down_left", "down_right", "jump_left", "jump_right"]  # impl:495
-TICK_CAP = 100000           # reference would hang/crash; we raise instead
+TICK_CAP = 4096             # per option, like TG_TICK_CAP: the reference would hang; we raise instead
 
 K_DOOR, K_HANDLE, K_KEY, K_BOLT, K_GOLD = range(5)
 _KIND_BY_WORD = {"door": K_DOOR, "handle": K_HANDLE, "key": K_KEY,
@@ -465,7 +465,7 @@ class OracleEnv:
             first = False
             tot += self.tick(act)
             n += 1
-            if n > TICK_CAP:
+            if n >= TICK_CAP and not done:
                 raise ReferenceWouldFail("option does not terminate")
         return tot
 
