@@ -259,6 +259,7 @@ def main():
     for k in range(W):
         env.step_raw(new_actions())
     env.clear_stats()
+    draws0 = int(env.get_state()["misc"][:, 3].to(torch.int64).sum().item())     # work accounting, outside the timed region
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -278,6 +279,7 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = env.launch_count - launches0
+    draws1 = int(env.get_state()["misc"][:, 3].to(torch.int64).sum().item())    # after the launch count was taken
     clocks = sampler.finish()
     per_step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = torch.tensor([sum(per_step_ms)], dtype=torch.float64, device=dev)
@@ -328,6 +330,7 @@ def main():
         "work": {"runnable_fraction": stats["runnable_steps"] / max(stats["gym_steps"], 1),
                  "primitive_ticks_per_step": stats["primitive_ticks"] / max(stats["gym_steps"], 1),
                  "primitive_ticks_per_s": stats["primitive_ticks"] / total_s if stats["gym_steps"] else None,
+                 "rng_draws_per_step_rank0": (draws1 - draws0) / max(n * K, 1),
                  "stats_all_ranks": stats},
         "wall_s_timed_region_incl_flush": t_wall,
     }
