@@ -26,7 +26,7 @@ struct Env {
     uint32_t draws;              // uniforms consumed by this env since creation
     uint32_t total_actions;      // impl:53,295 (per episode)
     // RNG
-    uint32_t blk, w0, w1, w2, w3;   // cached Philox block
+    uint32_t d0, w0, w1, w2, w3;    // draw index at the start of this API call, cached Philox block
     uint32_t key0, key1, id_lo, id_hi;
     const double *tape;             // parity mode: this env's slice of the draw tape
     // row-mask cache for the two probes every tick makes (valid while playery == m_py and the doors
@@ -55,9 +55,8 @@ __device__ __forceinline__ uint32_t bag_items(uint32_t f) {
 }
 
 // ---------------------------------------------------------------------------
-// RNG: Philox4x32-10, two 53-bit uniforms per block (same construction as
-// CPython's random(): (a>>5, b>>6) -> (a*2^26+b)/2^53).
-// ctr = (draw_index >> 1, 0, env_id_lo, env_id_hi), key = (seed_lo, seed_hi)
+// RNG: Philox4x32-10, four 32-bit uniforms per block (u = word / 2^32).
+// ctr = (d0, j >> 2, env_id_lo, env_id_hi), key = (seed_lo, seed_hi); word = j & 3 (see draw_k)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               uint32_t k0, uint32_t k1,
@@ -72,18 +71,25 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 
-// One uniform draw as the 53-bit integer k with u = k / 2^53 (exactly CPython's random()).
+// One uniform draw as the integer k with u = k / 2^53.  Tape mode: k is the recorded CPython double times
+// 2^53 (exact: MT outputs are multiples of 2^-53).  Philox mode: one 32-bit word per draw, u = w / 2^32,
+// i.e. k = w << 21, four draws per Philox4x32-10 block.  Blocks are numbered *per API call*: draw j of a call
+// that began at draw index d0 is word (j & 3) of block (d0, j >> 2) -- so every lane of a warp refills on
+// the same loop trip (j = 0, 4, 8 ...) however many draws its env consumed in earlier calls.  With blocks
+// numbered by the absolute draw index the refills of 32 lanes were spread over all trips and the warp
+// paid for the block function on nearly every tick (measured: 44 % of the time of a walking tick).
+// (d0, j >> 2) never repeats for one env: a call that consumed draws advances d0 past them.
+// Every transform of the reference is then applied to u exactly as CPython would (same thresholds, same
+// round-half-even); only the resolution of u is 2^-32.
 template <bool TAPE, int NI>
 __device__ __forceinline__ uint64_t draw_k(Env<NI> &e) {
     uint32_t d = e.draws++;
-    if (TAPE) return (uint64_t)__double2ull_rz(e.tape[d] * 9007199254740992.0);   // exact: MT outputs are multiples of 2^-53
-    uint32_t b = d >> 1;
-    if (b != e.blk) {
-        philox4x32_10(b, 0u, e.id_lo, e.id_hi, e.key0, e.key1, e.w0, e.w1, e.w2, e.w3);
-        e.blk = b;
-    }
-    uint32_t a = (d & 1u) ? e.w2 : e.w0, c = (d & 1u) ? e.w3 : e.w1;
-    return ((uint64_t)(a >> 5) << 26) | (uint64_t)(c >> 6);
+    if (TAPE) return (uint64_t)__double2ull_rz(e.tape[d] * 9007199254740992.0);
+    uint32_t j = d - e.d0;
+    if ((j & 3u) == 0u)
+        philox4x32_10(e.d0, j >> 2, e.id_lo, e.id_hi, e.key0, e.key1, e.w0, e.w1, e.w2, e.w3);
+    const uint32_t lo = (j & 1u) ? e.w1 : e.w0, hi = (j & 1u) ? e.w3 : e.w2;
+    return (uint64_t)((j & 2u) ? hi : lo) << 21;
 }
 __device__ __forceinline__ double k_to_unit(uint64_t k) { return (double)k * (1.0 / 9007199254740992.0); }   // exact
 template <bool TAPE, int NI>
@@ -756,7 +762,7 @@ __device__ __forceinline__ void load_env(Env<NI> &e, const BatchView &B, int64_t
     }
     e.draws = acct.x; e.total_actions = acct.w;
     row_cache_drop(e); e.m_fall = 0; e.m_side = 0;
-    e.blk = 0xFFFFFFFFu; e.w0 = e.w1 = e.w2 = e.w3 = 0;
+    e.d0 = acct.x; e.w0 = e.w1 = e.w2 = e.w3 = 0;
     e.key0 = B.seed_lo; e.key1 = B.seed_hi;
     uint64_t id = (uint64_t)(B.first_env_id + i);
     e.id_lo = (uint32_t)id; e.id_hi = (uint32_t)(id >> 32);

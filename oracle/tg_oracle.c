@@ -67,7 +67,7 @@ typedef struct {
     int64_t ep_return; int32_t ep_steps;
     int error;
     /* rng */
-    uint32_t draws;
+    uint32_t draws, d0;          /* d0: draw index when the current batch call began (Philox block numbering) */
     int64_t env_id;
 } env_t;
 
@@ -83,8 +83,9 @@ typedef struct {
 
 /* ---------------------------------------------------------------- RNG ---- */
 /* Philox4x32-10 (Salmon et al., SC'11), restated from the published round
- * function.  ctr = (draw_block, 0, env_id_lo, env_id_hi), key = (seed_lo, seed_hi).
- * Two 53-bit uniforms per block, built like MT genrand_res53 (CPython random()). */
+ * function.  Blocks are numbered per batch call: draw j of a call that began at draw index d0 is word (j & 3)
+ * of ctr = (d0, j >> 2, env_id_lo, env_id_hi), key = (seed_lo, seed_hi); u = w / 2^32 (the reference's
+ * transforms are applied to u unchanged).  Every tgo_batch_* entry point that can draw sets d0 first. */
 static void philox4x32_10(const uint32_t c[4], const uint32_t k[2], uint32_t out[4])
 {
     uint32_t c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], k0 = k[0], k1 = k[1];
@@ -107,11 +108,11 @@ static double draw(const batch_t *b, env_t *e)
         int64_t i = e - b->e;
         return b->tape[b->tape_off[i] + d];
     }
-    uint32_t c[4] = { d >> 1, 0u, (uint32_t)e->env_id, (uint32_t)((uint64_t)e->env_id >> 32) };
+    uint32_t j = d - e->d0;                          /* draw j of this batch call */
+    uint32_t c[4] = { e->d0, j >> 2, (uint32_t)e->env_id, (uint32_t)((uint64_t)e->env_id >> 32) };
     uint32_t k[2] = { (uint32_t)b->seed, (uint32_t)(b->seed >> 32) }, w[4];
     philox4x32_10(c, k, w);
-    uint32_t a = w[(d & 1) * 2] >> 5, bb = w[(d & 1) * 2 + 1] >> 6;
-    return (a * 67108864.0 + bb) * (1.0 / 9007199254740992.0);
+    return w[j & 3] * (1.0 / 4294967296.0);          /* one 32-bit word per draw: u = w / 2^32 (exact in a double) */
 }
 
 static double uniform(const batch_t *b, env_t *e, double lo, double hi)
@@ -566,6 +567,7 @@ void tgo_batch_reset(void *bp, const uint8_t *mask, double *obs)
 {
     batch_t *b = bp; int od = b->lv->obs_dim;
     for (int64_t i = 0; i < b->n; i++) {
+        b->e[i].d0 = b->e[i].draws;
         if (!mask || mask[i]) { b->e[i].error = 0; env_reset(b, &b->e[i]); }
         if (obs) write_obs(&b->e[i], obs + i * od);
     }
@@ -580,6 +582,7 @@ void tgo_batch_step(void *bp, const int32_t *actions, double *obs, float *reward
     for (int64_t i = 0; i < b->n; i++) {
         env_t *e = &b->e[i];
         int ran, nt, err0 = e->error;
+        e->d0 = e->draws;
         int r = run_option(b, e, actions[i], &ran, &nt);
         e->ep_return += r; e->ep_steps += 1;
         int term = is_done(e);
@@ -605,6 +608,7 @@ void tgo_batch_prim_step(void *bp, const int32_t *actions, double *obs, float *r
     for (int64_t i = 0; i < b->n; i++) {
         env_t *e = &b->e[i];
         int err0 = e->error;
+        e->d0 = e->draws;
         int r = tick(b, e, actions[i]);
         e->ep_return += r; e->ep_steps += 1;
         int term = is_done(e);
@@ -623,7 +627,7 @@ void tgo_batch_init_with_state(void *bp, const double *states, const uint8_t *ma
 {
     batch_t *b = bp; int od = b->lv->obs_dim;
     for (int64_t i = 0; i < b->n; i++)
-        if (!mask || mask[i]) env_init_with_state(b, &b->e[i], states + i * od);
+        if (!mask || mask[i]) { b->e[i].d0 = b->e[i].draws; env_init_with_state(b, &b->e[i], states + i * od); }
 }
 
 /* previously_triggered flag of every handle, [N][n_handles] */

@@ -238,3 +238,70 @@ def test_primitive_step_matches_c_oracle(VTG):
         if t % 150 == 149:
             assert_state_equal(env, cb, "tick %d" % t)
     assert list(env.stats().values()) == cb.stats().tolist()
+
+
+def test_philox_mode_statistics(VTG):
+    """Production RNG (Philox4x32-10, one 32-bit word per draw) drives the reference's transforms with
+    the right probabilities: noisy() (impl:361-366), the JUMP coin (impl:318), flip() (objs:117-122) and
+    the reset's handle angles (impl:99-104).  Exact law of noisy(-4) from the oracle's own code on a dense
+    grid of u; tolerances are 6 sigma of the binomial / sample-mean error at n = 262 144."""
+    n = 1 << 18
+    env = VTG(n, seed=2024, render=False, auto_reset=False)
+    full = lambda k: torch.full((n,), k, dtype=torch.int32, device="cuda")
+    env.reset()
+    st0 = env.get_state()
+    ang = st0["angles"].cpu().numpy()
+    up = st0["handles"].cpu().numpy().astype(bool)
+    nh = sum(1 for ob in po.default_level().objects if ob[0] == po.K_HANDLE)
+    for h in range(nh):
+        a = ang[:, h]
+        lo, hi = (0.85, 1.0) if up[0, h] else (0.0, 0.15)
+        assert a.min() >= lo and a.max() <= hi
+        assert abs(a.mean() - (lo + hi) / 2) < 6 * 0.15 / np.sqrt(12 * n)
+        hist = np.histogram(a, bins=16, range=(lo, hi))[0]
+        assert np.abs(hist - n / 16).max() < 6 * np.sqrt(n / 16)
+
+    # noisy(-INCR): law from the oracle's formula on 2^16 midpoints of u
+    o = po.OracleEnv(po.default_level(), lambda: 0.5)
+    law = {}
+    for i in range(1 << 16):
+        o._draw = lambda u=(i + 0.5) / 65536.0: u
+        d = o.noisy(-po.INCR)
+        law[d] = law.get(d, 0) + 1.0 / 65536
+    env.step_raw(full(3))                                   # down the first ladder: everyone is in a corridor
+    x0 = env.get_state()["pos"][:, 0].clone()
+    env.primitive_step(full(po.LEFT))
+    dx = (env.get_state()["pos"][:, 0] - x0).cpu().numpy()
+    assert set(np.unique(dx)) == set(law), (np.unique(dx), law)
+    for d, p in law.items():
+        assert abs((dx == d).mean() - p) < 6 * np.sqrt(p * (1 - p) / n), (d, p)
+
+    # JUMP: ticker 23 with probability 3/4 (u > 0.25), else 22; the same tick then consumes one.  The
+    # reference only jumps with the feet on the ground and head room: find such a state with the Python
+    # oracle (a random walk until a jump option is runnable) and restore it into every env.
+    import random as _random
+    r = _random.Random(0)
+    walker = po.OracleEnv(po.default_level(), r.random)
+    for _ in range(5000):
+        m = walker.mask()
+        if m[7] or m[8]:
+            break
+        walker.gym_step(r.choice([k for k in range(9) if m[k]]))
+    assert m[7] or m[8]
+    env.init_with_state(np.tile(np.asarray(walker.obs(), dtype=np.float64), (n, 1)))
+    env.primitive_step(full(po.JUMP))
+    tk = env.get_state()["misc"][:, 1].cpu().numpy()
+    assert set(np.unique(tk)) == {21, 22}
+    assert abs((tk == 22).mean() - 0.75) < 6 * np.sqrt(0.75 * 0.25 / n)
+
+    # flip(): walk to the first handle (closed-loop solver prefix: go_left reaches it), interact
+    env.reset()
+    env.step_raw(full(3)); env.step_raw(full(0))
+    m = env.available_mask.cpu().numpy()[:, 4].astype(bool)
+    assert m.mean() > 0.9, "go_left from the first ladder ends next to the first handle"
+    h0 = env.get_state()["handles"].cpu().numpy()
+    env.primitive_step(full(po.INTERACT))
+    h1 = env.get_state()["handles"].cpu().numpy()
+    flipped = (h0 != h1).any(axis=1)[m]
+    assert abs(flipped.mean() - 0.8) < 6 * np.sqrt(0.8 * 0.2 / m.sum())
+    env.close()

@@ -83,28 +83,37 @@ def test_c_oracle_philox_mode_matches_py_oracle_with_same_uniforms():
     b.reset()
     rng = np.random.default_rng(0)
 
-    def uniforms(env_id):
-        d = 0
-        while True:
-            w = c_oracle.philox([d >> 1, 0, env_id & 0xffffffff, env_id >> 32], [seed & 0xffffffff, seed >> 32])
-            a, bb = int(w[(d & 1) * 2]) >> 5, int(w[(d & 1) * 2 + 1]) >> 6
-            yield (a * 67108864.0 + bb) / 9007199254740992.0
-            d += 1
+    class Stream:
+        """draw j of an API call that began at draw index d0 = word j&3 of Philox(ctr=(d0, j>>2, env id), key=seed)"""
+        def __init__(self, env_id):
+            self.env_id, self.d, self.d0 = env_id, 0, 0
 
-    envs = []
+        def begin_call(self):
+            self.d0 = self.d
+
+        def __call__(self):
+            j = self.d - self.d0
+            self.d += 1
+            w = c_oracle.philox([self.d0, j >> 2, self.env_id & 0xffffffff, self.env_id >> 32],
+                                [seed & 0xffffffff, seed >> 32])
+            return int(w[j & 3]) / 4294967296.0
+
+    envs, streams = [], []
     for i in range(n):
-        g = uniforms(first + i)
+        g = Stream(first + i)
         e = po.OracleEnv.__new__(po.OracleEnv)
-        e.level, e.u = lvt, g.__next__
+        e.level, e.u = lvt, g
         e.ch, e.cw = len(lvt.tiles), len(lvt.tiles[0])
         e.width, e.height, e.draws = e.cw * po.S, e.ch * po.S, 0
         e.reset()
         envs.append(e)
+        streams.append(g)
     for t in range(60):
         m = b.mask()
         acts = [int(rng.choice(np.flatnonzero(m[i]))) if t % 2 else int(rng.integers(9)) for i in range(n)]
         obs, rew, done, ran, ticks = b.step(acts)
         for i, e in enumerate(envs):
+            streams[i].begin_call()
             o2, r2, d2, _ = e.gym_step(acts[i])
             assert obs[i].tolist() == o2
             assert (r2 is None) == (not ran[i]) and int(rew[i]) == (r2 or 0)
