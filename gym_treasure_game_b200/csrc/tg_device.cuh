@@ -81,15 +81,18 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 // (d0, j >> 2) never repeats for one env: a call that consumed draws advances d0 past them.
 // Every transform of the reference is then applied to u exactly as CPython would (same thresholds, same
 // round-half-even); only the resolution of u is 2^-32.
-template <bool TAPE, int NI>
-__device__ __forceinline__ uint64_t draw_k(Env<NI> &e) {
-    uint32_t d = e.draws++;
-    if (TAPE) return (uint64_t)__double2ull_rz(e.tape[d] * 9007199254740992.0);
-    uint32_t j = d - e.d0;
+template <int NI>
+__device__ __forceinline__ uint32_t draw_w(Env<NI> &e) {           // Philox mode: the 32-bit word of the next draw
+    uint32_t j = e.draws++ - e.d0;
     if ((j & 3u) == 0u)
         philox4x32_10(e.d0, j >> 2, e.id_lo, e.id_hi, e.key0, e.key1, e.w0, e.w1, e.w2, e.w3);
     const uint32_t lo = (j & 1u) ? e.w1 : e.w0, hi = (j & 1u) ? e.w3 : e.w2;
-    return (uint64_t)((j & 2u) ? hi : lo) << 21;
+    return (j & 2u) ? hi : lo;
+}
+template <bool TAPE, int NI>
+__device__ __forceinline__ uint64_t draw_k(Env<NI> &e) {
+    if (TAPE) return (uint64_t)__double2ull_rz(e.tape[e.draws++] * 9007199254740992.0);
+    return (uint64_t)draw_w(e) << 21;
 }
 __device__ __forceinline__ double k_to_unit(uint64_t k) { return (double)k * (1.0 / 9007199254740992.0); }   // exact
 template <bool TAPE, int NI>
@@ -330,8 +333,13 @@ __device__ __forceinline__ int noisy_from_k(uint64_t k, bool negative) {
     const int r = (int)(m > (1ull << 50)) + (int)(m >= (3ull << 50));
     return (negative ? -4 : 2) + r;
 }
+// For k = w << 21 (Philox mode) the same function in 32-bit arithmetic: q = w << 20, k & q & 1 = 0, m = w << 20.
+__device__ __forceinline__ int noisy_r_from_w(uint32_t w) { return (int)(w > (1u << 30)) + (int)(w >= (3u << 30)); }
 template <bool TAPE, int NI>
-__device__ __forceinline__ int noisy(Env<NI> &e, bool negative) { return noisy_from_k(draw_k<TAPE>(e), negative); }
+__device__ __forceinline__ int noisy(Env<NI> &e, bool negative) {
+    if (TAPE) return noisy_from_k(draw_k<true>(e), negative);
+    return (negative ? -4 : 2) + noisy_r_from_w(draw_w(e));
+}
 
 // impl:350-354: key / gold within 24 px of (playerx, playery + 24) go to the next bag cell, item (= file) order
 template <int NI>
@@ -499,6 +507,47 @@ __device__ __forceinline__ bool option_setup(const Env<NI> &e, const LevelBlob &
     return false;      // out-of-range action: the reference raises IndexError (tg:92); we report "not run"
 }
 
+// Conservative extent of the "nothing can happen" stretch of a go_left / go_right walk (ticker == 0, row masks
+// mside / mfall valid for e.py).  Returns the farthest x in direction s such that at every player x' between
+// e.px and x (inclusive): the ground holds (impl:283-288 false), the side probe is free (impl:259-281), the
+// option's target is not yet reached (opts:69-72) and no key / gold is within pick-up range (impl:350-354).
+// If e.px itself fails one of these the result lies behind the player (e.px - s).
+// Cell c of the padded grid covers pixels [48c - 144, 48c - 97] (pad_cell).
+template <int NI>
+__device__ __forceinline__ int walk_safe_bound(const Env<NI> &e, const LevelBlob &L, int s, int tpx,
+                                               uint32_t mside, uint32_t mfall) {
+    const int px = e.px, behind = px - s, FAR = 1 << 20;
+    const int a = pad_cell(px - 10), b = pad_cell(px + 10);
+    if ((((mfall >> a) | (mfall >> b)) & 1u) == 0u) return behind;            // would fall now
+    if (abs(tpx - px) < 4) return behind;                                        // aligned now
+    int bound;
+    if (s > 0) {
+        bound = (px <= tpx - 4) ? tpx - 4 : FAR;
+        const int c0 = pad_cell(px + 16);
+        const uint32_t blk = mside >> c0;                                         // first blocking cell at / right of c0
+        if (blk) bound = min(bound, 48 * (c0 + __ffs(blk) - 1) - 144 - 16 - 1);
+        const uint32_t hole = ~mfall >> (a + 1);                                  // both probes over open cells: x - 10 enters it
+        if (hole) bound = min(bound, 48 * (a + __ffs(hole)) - 144 + 10 - 1);
+    } else {
+        bound = (px >= tpx + 4) ? tpx + 4 : -FAR;
+        const int c0 = pad_cell(px - 16);
+        const uint32_t blk = mside << (31 - c0);                                  // bit c0 -> bit 31
+        if (blk) bound = max(bound, 48 * (c0 - __clz(blk)) - 144 + 47 + 16 + 1);
+        const uint32_t hole = ~mfall << (32 - b);                                 // bit b-1 -> bit 31 (b >= 3)
+        if (hole) bound = max(bound, 48 * (b - 1 - __clz(hole)) - 144 + 47 - 10 + 1);
+    }
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+        if (i >= L.n_items) continue;
+        const int dy = e.py - e.iy[i], c = e.ix[i] + S / 2;
+        if (dy * dy >= 24 * 24) continue;                                         // never in range on this row
+        if (px < c - 23) { if (s > 0) bound = min(bound, c - 24); }               // |x - c| <= 23 contains every x in range
+        else if (px > c + 23) { if (s < 0) bound = max(bound, c + 24); }
+        else return behind;
+    }
+    return bound;
+}
+
 // Runs option k (already known to be runnable, target column tcx from option_setup) to
 // termination.  Returns the number of primitive ticks; reward = -ticks - 4*[jump option]
 // (impl:15-16,356-359).
@@ -517,18 +566,40 @@ __device__ __forceinline__ int run_option_to_end(Env<NI> &e, const LevelBlob &L,
         if (e.m_py != e.py) fall_cache_fill(e, L);
         if (e.m_py_side != e.py) side_cache_fill(e, L);
         const uint32_t mside = e.m_side, mfall = e.m_fall;
-        while (!done && ticker(e.flags) == 0 &&
-               (((mfall >> pad_cell(e.px - 10)) | (mfall >> pad_cell(e.px + 10))) & 1u) != 0u) {
+        // Inside [px .. bound] (walk_safe_bound) a tick is just "count, move by noisy()": no probe can change,
+        // the target is not reached, nothing can be picked up.  Such ticks run without any check as long as the
+        // largest move (4 px) cannot leave the interval; the ticks around an event take the checked form below.
+        int bound = ticker(e.flags) == 0 ? walk_safe_bound(e, L, s, tpx, mside, mfall) : e.px - s;
+        for (;;) {
+            if (s * (bound - e.px) >= 4) {
+                if (!TAPE) {
+                    // one Philox block = four ticks
+                    while (s * (bound - e.px) >= 16 && ((e.draws - e.d0) & 3u) == 0u && n <= TG_TICK_CAP - 4) {
+                        uint32_t a, b, c, d;
+                        philox4x32_10(e.d0, (e.draws - e.d0) >> 2, e.id_lo, e.id_hi, e.key0, e.key1, a, b, c, d);
+                        e.draws += 4; n += 4;
+                        e.px += (s < 0 ? -16 : 8) + noisy_r_from_w(a) + noisy_r_from_w(b) + noisy_r_from_w(c) + noisy_r_from_w(d);
+                    }
+                }
+                while (s * (bound - e.px) >= 4 && n < TG_TICK_CAP) { e.px += noisy<TAPE>(e, s < 0); n++; }
+                e.flags = (e.flags & ~(1u << F_FACING)) | (s < 0 ? 0u : (1u << F_FACING));
+                if (n >= TG_TICK_CAP) { e.total_actions += n; e.flags |= 1u << F_ERROR; return n; }
+            }
+            if (ticker(e.flags) != 0 ||
+                (((mfall >> pad_cell(e.px - 10)) | (mfall >> pad_cell(e.px + 10))) & 1u) == 0u) break;
             done = abs(tpx - e.px) < 4;                   // opts:80-85: the action of the final policy step still runs
-            e.total_actions++;
+            const int len0 = bag_len(e.flags);
             if (((mside >> pad_cell(e.px + 16 * s)) & 1u) == 0u) {
                 e.px += noisy<TAPE>(e, s < 0);
                 e.flags = (e.flags & ~(1u << F_FACING)) | (s < 0 ? 0u : (1u << F_FACING));
             }
             pickups(e, L);
             n++;
-            if (n >= TG_TICK_CAP && !done) { e.flags |= 1u << F_ERROR; return n; }
+            if (done) break;
+            if (n >= TG_TICK_CAP) { e.total_actions += n; e.flags |= 1u << F_ERROR; return n; }
+            if (s * (e.px - bound) > 0 || bag_len(e.flags) != len0) bound = walk_safe_bound(e, L, s, tpx, mside, mfall);
         }
+        e.total_actions += n;
         if (done) return n;
     }
     do {
