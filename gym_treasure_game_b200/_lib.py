@@ -8,7 +8,10 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from ._build import SO
+from ._build import SO as _DEFAULT_SO
+
+# TG_B200_LIB selects another build of the same library (kernel tuning experiments)
+SO = os.environ.get("TG_B200_LIB") or _DEFAULT_SO
 
 MAX_DOORS, MAX_HANDLES, MAX_BOLTS, MAX_ITEMS = 6, 4, 3, 4
 MAX_OBJECTS, MAX_TRIGGERS, MAX_GRID, MAX_LEVELS = 16, 32, 26, 8
@@ -67,6 +70,7 @@ _SIGNATURES = {
     "tg_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tg_stats_clear": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tg_launch_count": (C.c_int64, [C.c_void_p]),
+    "tg_debug_phase_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

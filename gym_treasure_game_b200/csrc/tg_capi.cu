@@ -104,6 +104,8 @@ extern "C" int tg_level_create(const uint8_t *tiles, int32_t cw, int32_t ch, con
     if (b.start_px < 0) { lv->info.start_cx = lv->info.start_cy = -1; }
     uint32_t flags = 1u << F_FACING;
     int obs = 2;
+    memset(b.obs_prog, OP_ZERO << 4, sizeof b.obs_prog);
+    b.obs_prog[0] = OP_PX << 4; b.obs_prog[1] = OP_PY << 4;
     int obj_of[5][TG_MAX_OBJECTS];
     int cnt[5] = {0, 0, 0, 0, 0};
     int n_items = 0;
@@ -132,7 +134,7 @@ extern "C" int tg_level_create(const uint8_t *tiles, int32_t cw, int32_t ch, con
             code |= TC_STATIC_OBJ;
             b.handle_cx[idx] = (int8_t)ob.cx; b.handle_cy[idx] = (int8_t)ob.cy; b.handle_obj[idx] = (uint8_t)o;
             if (ob.flag) flags |= 1u << (F_HANDLES + idx);
-            b.obj_obs[o] = (uint8_t)obs; obs += 1;
+            b.obj_obs[o] = (uint8_t)obs; b.obs_prog[obs] = (uint8_t)(OP_ANGLE << 4 | idx); obs += 1;
             b.n_handles++;
             break;
         case TG_BOLT:
@@ -141,7 +143,7 @@ extern "C" int tg_level_create(const uint8_t *tiles, int32_t cw, int32_t ch, con
             code |= TC_STATIC_OBJ;
             b.bolt_cx[idx] = (int8_t)ob.cx; b.bolt_cy[idx] = (int8_t)ob.cy; b.bolt_obj[idx] = (uint8_t)o;
             if (ob.flag) flags |= 1u << (F_BOLTS + idx);
-            b.obj_obs[o] = (uint8_t)obs; obs += 1;
+            b.obj_obs[o] = (uint8_t)obs; b.obs_prog[obs] = (uint8_t)(OP_BOLT << 4 | idx); obs += 1;
             b.n_bolts++;
             break;
         default:   // key, gold
@@ -149,7 +151,8 @@ extern "C" int tg_level_create(const uint8_t *tiles, int32_t cw, int32_t ch, con
             if (idx >= TG_MAX_ITEMS) { delete lv; return fail(TG_ERR_ARG, "more than %d keys+gold", TG_MAX_ITEMS); }
             b.item_cx[idx] = (int8_t)ob.cx; b.item_cy[idx] = (int8_t)ob.cy; b.item_obj[idx] = (uint8_t)o;
             if (ob.kind == TG_KEY) b.key_mask |= (uint8_t)(1u << idx); else b.gold_mask |= 1u << idx;
-            b.obj_obs[o] = (uint8_t)obs; obs += 2;
+            b.obj_obs[o] = (uint8_t)obs;
+            b.obs_prog[obs] = (uint8_t)(OP_IX << 4 | idx); b.obs_prog[obs + 1] = (uint8_t)(OP_IY << 4 | idx); obs += 2;
             n_items++;
             break;
         }
@@ -157,6 +160,11 @@ extern "C" int tg_level_create(const uint8_t *tiles, int32_t cw, int32_t ch, con
         cnt[ob.kind]++;
     }
     b.n_items = (uint8_t)n_items; b.n_objs = (uint8_t)n_objs; b.obs_dim = (uint8_t)obs;
+    {   // obs_prog[31] = 1: slot order of the shipped level (write_obs has straight-line code for it)
+        static const uint8_t shipped[9] = {OP_PX << 4, OP_PY << 4, OP_ANGLE << 4 | 0, OP_ANGLE << 4 | 1, OP_IX << 4 | 0,
+                                           OP_IY << 4 | 0, OP_BOLT << 4 | 0, OP_IX << 4 | 1, OP_IY << 4 | 1};
+        b.obs_prog[31] = (obs == 9 && memcmp(b.obs_prog, shipped, 9) == 0) ? 1 : 0;
+    }
     b.init_flags = flags;
     // bag slots are the cells (cw-1-k, ch-1) (impl:353); they must be unreachable, i.e. plain WALL,
     // so that an item in the bag can never be picked up a second time
@@ -309,6 +317,20 @@ extern "C" int tg_create(const tg_level *const *levels, int32_t n_levels, const 
         CUE(dev_alloc(e, &d_ids, (size_t)num_envs));
         CUE(cudaMemcpy(d_ids, level_ids, (size_t)num_envs, cudaMemcpyHostToDevice));
         B.level_id = d_ids;
+    }
+    {   // quotient tables of the observation (impl:368-378): float32 of the reference's float64 x / width, y / height
+        std::vector<float> lut((size_t)n_levels * 2 * OBS_LUT_N);
+        for (int l = 0; l < n_levels; l++) {
+            const double W = (double)levels[l]->info.frame_w, H = (double)levels[l]->info.frame_h;
+            for (int v = 0; v < OBS_LUT_N; v++) {
+                lut[((size_t)l * 2 + 0) * OBS_LUT_N + v] = (float)((double)(v - S) / W);
+                lut[((size_t)l * 2 + 1) * OBS_LUT_N + v] = (float)((double)(v - S) / H);
+            }
+        }
+        float *d_lut = nullptr;
+        CUE(dev_alloc(e, &d_lut, lut.size()));
+        CUE(cudaMemcpy(d_lut, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice));
+        B.obs_lut = d_lut;
     }
     CUE(dev_alloc(e, &B.stats, (size_t)8));
     CUE(cudaMemset(B.stats, 0, 64));
@@ -483,6 +505,12 @@ extern "C" int tg_set_draw_tape(tg_env *env, const double *tape, const int64_t *
     env->B.tape = tape; env->B.tape_off = offsets;
     // draw indices restart at 0: acct.x is the first word of each 16-byte record
     CU(cudaMemset2DAsync(env->B.acct, sizeof(uint4), 0, sizeof(uint32_t), (size_t)env->B.n, (cudaStream_t)stream));
+    return TG_OK;
+}
+
+extern "C" int tg_debug_phase_buffer(tg_env *env, uint64_t *stamps) {
+    if (!env) return fail(TG_ERR_ARG, "null env");
+    env->B.phase_ts = reinterpret_cast<unsigned long long *>(stamps);
     return TG_OK;
 }
 

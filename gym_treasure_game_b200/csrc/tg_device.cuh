@@ -712,28 +712,48 @@ __device__ __forceinline__ void reset_env(Env<NI> &e, const LevelBlob &L) {
 // ---------------------------------------------------------------------------
 // observation  (impl:368-378 + objs get_state): float64 arithmetic, stored as float32
 // ---------------------------------------------------------------------------
+// One table look-up per coordinate: lut = this level's pair of tables (BatchView::obs_lut), lut[0][v + S] =
+// float32(v / W), lut[1][v + S] = float32(v / H) -- the reference's float64 quotient (impl:370-371, objs get_state)
+// rounded to float32, filled on the host.  Coordinates outside the tables (only reachable through injected item
+// positions) take one IEEE float division, which gives the same value: for these small integers the correctly
+// rounded float32 quotient equals the float64 quotient rounded to float32 (the quotient is a multiple of
+// 1/(W*2^k) away from every rounding boundary, far more than 2^-53).  The slot layout comes from the level's
+// observation program (LevelBlob::obs_prog), so there is no per-object dispatch here.
+__device__ __forceinline__ float obs_quot(const float *__restrict__ lut, int v, int extent) {
+    const unsigned idx = (unsigned)(v + S);
+    return idx < (unsigned)OBS_LUT_N ? __ldg(lut + idx) : __fdiv_rn((float)v, (float)extent);
+}
+// pre0, pre1 (npre of them valid) = angles of the first handles already in registers (requested together with the state).
 template <int NI>
-__device__ __forceinline__ void write_obs(const Env<NI> &e, const LevelBlob &L, float *o, int obs_dim) {
-    // float(px) / width is computed in float64 by the reference and stored here as float32.  For these
-    // small integers the correctly rounded float32 quotient equals the float64 quotient rounded to float32
-    // (the quotient is a multiple of 1/(W*2^k) away from every rounding boundary, far more than 2^-53),
-    // so one IEEE float division gives the identical value (tests compare against the float64 oracle).
-    const float W = (float)(L.cw * S), H = (float)(L.ch * S);
-    int k = 0;
-    o[k++] = __fdiv_rn((float)e.px, W);
-    o[k++] = __fdiv_rn((float)e.py, H);
-    for (int j = 0; j < L.n_objs; j++) {
-        int kind = L.obj_kind[j], i = L.obj_idx[j];
-        if (kind == TG_HANDLE) o[k++] = (float)e.angles[(int64_t)i * e.n];
-        else if (kind == TG_BOLT) o[k++] = ((e.flags >> (F_BOLTS + i)) & 1u) ? 1.0f : 0.0f;
-        else if (kind == TG_KEY || kind == TG_GOLD) {
+__device__ __forceinline__ void write_obs(const Env<NI> &e, const LevelBlob &L, const float *__restrict__ lut,
+                                          float *__restrict__ o, int obs_dim, int npre = 0, double pre0 = 0.0, double pre1 = 0.0) {
+    const int W = L.cw * S, H = L.ch * S;
+    const int nk = L.obs_dim;
+    if (L.obs_prog[31] == 1) {       // the shipped layout's slot order (two handles, key, bolt, gold): straight-line code
+        const float *lx = lut, *ly = lut + OBS_LUT_N;
+        const double a0 = (npre > 0) ? pre0 : e.angles[0], a1 = (npre > 1) ? pre1 : e.angles[e.n];
+        o[0] = obs_quot(lx, e.px, W); o[1] = obs_quot(ly, e.py, H);
+        o[2] = (float)a0; o[3] = (float)a1;
+        o[4] = obs_quot(lx, e.ix[0], W); o[5] = obs_quot(ly, e.iy[0], H);
+        o[6] = ((e.flags >> F_BOLTS) & 1u) ? 1.0f : 0.0f;
+        o[7] = obs_quot(lx, e.ix[NI > 1 ? 1 : 0], W); o[8] = obs_quot(ly, e.iy[NI > 1 ? 1 : 0], H);
+        for (int k = 9; k < obs_dim; k++) o[k] = 0.0f;
+        return;
+    }
+    for (int k = 0; k < nk; k++) {
+        const int p = L.obs_prog[k], op = p >> 4, i = p & 15;
+        float v;
+        if (op >= OP_IX) {
             int x = 0, y = 0;
 #pragma unroll
             for (int q = 0; q < NI; q++) if (q == i) { x = e.ix[q]; y = e.iy[q]; }
-            o[k++] = __fdiv_rn((float)x, W); o[k++] = __fdiv_rn((float)y, H);
-        }
+            v = (op == OP_IX) ? obs_quot(lut, x, W) : obs_quot(lut + OBS_LUT_N, y, H);
+        } else if (op == OP_ANGLE) v = (float)((i < npre) ? (i == 0 ? pre0 : pre1) : e.angles[(int64_t)i * e.n]);
+        else if (op == OP_BOLT) v = ((e.flags >> (F_BOLTS + i)) & 1u) ? 1.0f : 0.0f;
+        else v = (op == OP_PX) ? obs_quot(lut, e.px, W) : obs_quot(lut + OBS_LUT_N, e.py, H);
+        o[k] = v;
     }
-    for (; k < obs_dim; k++) o[k] = 0.0f;
+    for (int k = nk; k < obs_dim; k++) o[k] = 0.0f;
 }
 
 template <int NI>
@@ -839,6 +859,26 @@ __device__ __forceinline__ void load_env(Env<NI> &e, const BatchView &B, int64_t
     e.id_lo = (uint32_t)id; e.id_hi = (uint32_t)(id >> 32);
     e.tape = B.tape ? B.tape + B.tape_off[i] : nullptr;
     e.angles = B.angles + i; e.n = B.n;
+}
+
+template <int NI>
+__device__ __forceinline__ void store_core(const Env<NI> &e, const BatchView &B, int64_t i) {
+    uint4 c;
+    c.x = pack_player(e.px, e.py, e.sticky); c.y = e.flags;
+    c.z = pack_xy(e.ix[0], e.iy[0]);
+    c.w = (NI > 1) ? pack_xy(e.ix[1], e.iy[1]) : 0u;
+    B.core[i] = c;
+    if (NI > 2) {
+        uint2 h;
+        h.x = pack_xy(e.ix[2], e.iy[2]);
+        h.y = (NI > 3) ? pack_xy(e.ix[3], e.iy[3]) : 0u;
+        B.items23[i] = h;
+    }
+}
+template <int NI>
+__device__ __forceinline__ void store_acct(const Env<NI> &e, const BatchView &B, int64_t i, uint4 acct) {
+    acct.x = e.draws; acct.w = e.total_actions;
+    B.acct[i] = acct;
 }
 
 template <int NI>

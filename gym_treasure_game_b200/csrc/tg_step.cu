@@ -51,17 +51,54 @@ constexpr int STEP_THREADS = TG_STEP_THREADS;
 constexpr int AUX_THREADS = 128;       // reset / mask kernels
 constexpr int NBUCKET = 64;          // length classes for the in-tile sort (bucket 0 = longest, 63 = not runnable)
 
+// debug instrumentation (tg_debug_phase_buffer): thread 0 of every CTA stamps the phase boundaries
+__device__ __forceinline__ void phase_stamp(const BatchView &B, int slot) {
+    if (B.phase_ts && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        B.phase_ts[(size_t)blockIdx.x * 8 + slot] = t;
+    }
+}
+
 // info word per env of the tile: bit 0 runnable, bit 1 reference-would-raise, bits 2-7 target column + 8,
-// bits 8-13 bucket
-__device__ __forceinline__ uint32_t pack_info(bool ran, bool err, int tcx, int bucket) {
-    return (ran ? 1u : 0u) | (err ? 2u : 0u) | ((uint32_t)((tcx + 8) & 63) << 2) | ((uint32_t)bucket << 8);
+// bits 8-13 bucket, bits 14-17 option id (9 = not an option id)
+__device__ __forceinline__ uint32_t pack_info(bool ran, bool err, int tcx, int bucket, int a) {
+    return (ran ? 1u : 0u) | (err ? 2u : 0u) | ((uint32_t)((tcx + 8) & 63) << 2) | ((uint32_t)bucket << 8) | ((uint32_t)a << 14);
+}
+
+// Reset of an env whose option did not run (time limit): out of line and through memory, so that the common
+// path of phase 4 carries neither the RNG state nor the Box-Muller code.  The caller has stored acct.
+// `drawn` = uniforms the env has already consumed in this call (its option ran): the Philox blocks of a call are
+// numbered from the call's first draw (draw_w), so the reset continues that numbering.
+template <bool TAPE, int NI>
+__device__ __noinline__ void reset_in_memory(const BatchView &B, const LevelBlob *L, int64_t i, uint32_t drawn) {
+    Env<NI> e;
+    uint4 acct;
+    load_env(e, B, i, acct);
+    e.d0 = e.draws - drawn;
+    if (!TAPE && (drawn & 3u)) philox4x32_10(e.d0, drawn >> 2, e.id_lo, e.id_hi, e.key0, e.key1, e.w0, e.w1, e.w2, e.w3);
+    reset_env<TAPE>(e, *L);
+    store_env(e, B, i, acct);
+}
+
+// exclusive scan of hist[0 .. 63] by warp 0 (two entries per lane)
+__device__ __forceinline__ void scan64(int *hist, int lane) {
+    const int v0 = hist[2 * lane], v1 = hist[2 * lane + 1];
+    int incl = v0 + v1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+    const int excl = incl - (v0 + v1);
+    hist[2 * lane] = excl; hist[2 * lane + 1] = excl + v0;
 }
 
 // ---------------------------------------------------------------------------
-// tg_step_kernel: one CTA owns a tile of TILE consecutive environments.
-//   phase 1  every env: evaluate can_run of the chosen option (+ target column) and estimate its
-//            length in ticks; histogram the length classes            (all lanes busy, short)
-//   phase 2  counting sort of the tile by length class -> perm[]       (shared-memory atomics)
+// tg_step_kernel: one CTA owns a tile of `tile` (<= TILE) consecutive environments.
+//   phase 0  counting sort of the tile by option id -> perm0[]: the classification below is a 9-way switch
+//            on the option, and with i.i.d. actions a warp in index order runs every case with 3-4 lanes
+//            (measured: can_run + length estimate were 30 % of the kernel's warp instructions at 2-6 active lanes)
+//   phase 1  in option order: evaluate can_run of the chosen option (+ target column), estimate its
+//            length in ticks; histogram the (code path, length) classes
+//   phase 2  counting sort of the tile by class -> perm[]                (shared-memory atomics)
 //   phase 3  warps pull 32-env chunks of perm[] from a shared counter; a lane runs its env's option
 //            to termination, then reward / done / time-limit / auto-reset / obs / stores.
 // Sorting puts the ~10-20 % runnable envs of a tile into a few full warps of similar length
@@ -73,7 +110,7 @@ __device__ __forceinline__ uint32_t pack_info(bool ran, bool err, int tcx, int b
 #endif
 template <bool TAPE, int NI, int TILE>
 __global__ void __launch_bounds__(STEP_THREADS, TG_STEP_MIN_BLOCKS)
-tg_step_kernel(BatchView B, const int32_t *__restrict__ actions, float *__restrict__ obs,
+tg_step_kernel(const __grid_constant__ BatchView B, int tile, const int32_t *__restrict__ actions, float *__restrict__ obs,
                float *__restrict__ reward, uint8_t *__restrict__ done_out, uint8_t *__restrict__ ran_out,
                uint16_t *__restrict__ avail_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -81,64 +118,113 @@ tg_step_kernel(BatchView B, const int32_t *__restrict__ actions, float *__restri
     __shared__ uint64_t bar;
     __shared__ int sh_stats[8];
     __shared__ int hist[NBUCKET];
-    __shared__ int next_chunk;
+    __shared__ int next_chunk, ready_head, ready_tail;
+    __shared__ int pending[TILE / 32];          // runnable envs of each 32-env index chunk that have not finished yet
+    __shared__ uint16_t ready[TILE / 32];       // queue of complete index chunks (0xFFFF = slot not filled yet)
     __shared__ uint32_t info[TILE];
+    __shared__ uint16_t perm0[TILE];
     __shared__ uint16_t perm[TILE];
     const int tid = threadIdx.x, lane = tid & 31;
+    phase_stamp(B, 0);
     if (tid < 8) sh_stats[tid] = 0;
     if (tid < NBUCKET) hist[tid] = 0;
-    if (tid == 0) next_chunk = 0;
+    if (tid == 0) { next_chunk = 0; ready_head = 0; ready_tail = 0; }
+    if (tid < TILE / 32) { pending[tid] = 0; ready[tid] = 0xFFFF; }
     stage_levels(levels, B.levels, B.n_levels, &bar);      // contains a __syncthreads()
+    phase_stamp(B, 1);
 
-    const int64_t base = B.r_begin + (int64_t)blockIdx.x * TILE;
-    const int count = (int)min((int64_t)TILE, B.r_begin + B.r_count - base);
+    const int64_t base = B.r_begin + (int64_t)blockIdx.x * tile;
+    const int count = (int)min((int64_t)tile, B.r_begin + B.r_count - base);
 
-    // ---- phase 1: classify ------------------------------------------------
-    for (int el = tid; el < count; el += STEP_THREADS) {
-        const int64_t i = base + el;
-        const LevelBlob &L = levels[B.level_id ? B.level_id[i] : 0];
-        Env<NI> e;
-        load_core(e, B, i);
-        const int a = actions[i];
-        int tcx; bool err;
-        const bool ran = option_setup(e, L, a, tcx, err);
-        // sort key: code-path class major (lanes of a warp then run the same policy and the same branch of
-        // tick()), estimated length minor (longest first); 63 = not runnable
-        int bucket = NBUCKET - 1;
-        if (ran) {
-            const int cls = (a <= TG_GO_RIGHT) ? 0 : (a <= TG_DOWN_LADDER) ? 1 : (a == TG_INTERACT) ? 4 : (a <= TG_DOWN_RIGHT) ? 2 : 3;
-            bucket = cls * 12 + 11 - min(estimate_ticks(e, L, a, tcx) / 10, 11);
-        }
-        info[el] = pack_info(ran, err, tcx, bucket);
-        atomicAdd(&hist[bucket], 1);
-    }
-    __syncthreads();
-    // ---- phase 2: exclusive scan of the 64 class counts (warp 0), then scatter ----
-    if (tid < 32) {
-        const int v0 = hist[2 * lane], v1 = hist[2 * lane + 1];
-        int incl = v0 + v1;
+    // Global loads of one phase are issued in batches before their first use: a dependent access costs about 1 us
+    // here (measured with tg_debug_phase_buffer), and one element per thread at a time left the SM waiting on it.
+    // ---- phase 0: sort by option id -------------------------------------------
+    for (int k0 = 0; k0 < count; k0 += 8 * STEP_THREADS) {
+        int av[8];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
-        const int excl = incl - (v0 + v1);
-        hist[2 * lane] = excl; hist[2 * lane + 1] = excl + v0;
+        for (int u = 0; u < 8; u++) { const int el = k0 + u * STEP_THREADS + tid; av[u] = (el < count) ? actions[base + el] : 0; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int el = k0 + u * STEP_THREADS + tid;
+            if (el < count) {
+                const int ac = ((unsigned)av[u] < (unsigned)TG_NUM_OPTIONS) ? av[u] : TG_NUM_OPTIONS;   // tg:92 raises IndexError; here: not run
+                info[el] = (uint32_t)ac;
+                atomicAdd(&hist[ac], 1);
+            }
+        }
     }
+    __syncthreads();
+    if (tid < 32) scan64(hist, lane);
+    __syncthreads();
+    for (int el = tid; el < count; el += STEP_THREADS) perm0[atomicAdd(&hist[info[el]], 1)] = (uint16_t)el;
+    __syncthreads();
+    if (tid < NBUCKET) hist[tid] = 0;
+    __syncthreads();
+    phase_stamp(B, 2);
+
+    // ---- phase 1: classify, in option order -------------------------------------
+    for (int j0 = 0; j0 < count; j0 += 4 * STEP_THREADS) {
+        uint4 cv[4];
+        int elv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int j = j0 + u * STEP_THREADS + tid;
+            elv[u] = (j < count) ? perm0[j] : -1;
+            if (elv[u] >= 0) cv[u] = B.core[base + elv[u]];
+        }
+#pragma unroll 1
+        for (int u = 0; u < 4; u++) {       // one copy of the classification code: pick the element with selects
+            const int el = (u == 0) ? elv[0] : (u == 1) ? elv[1] : (u == 2) ? elv[2] : elv[3];
+            if (el < 0) continue;
+            const uint4 cu = (u == 0) ? cv[0] : (u == 1) ? cv[1] : (u == 2) ? cv[2] : cv[3];
+            const int64_t i = base + el;
+            const LevelBlob &L = levels[B.level_id ? B.level_id[i] : 0];
+            Env<NI> e;
+            load_core(e, B, i, cu);
+            const int a = (int)info[el];
+            int tcx; bool err;
+            const bool ran = option_setup(e, L, a, tcx, err);
+            // sort key: code-path class major (lanes of a warp then run the same policy and the same branch of
+            // tick()), estimated length minor (longest first); 63 = not runnable
+            int bucket = NBUCKET - 1;
+            if (ran) {
+                const int cls = (a <= TG_GO_RIGHT) ? 0 : (a <= TG_DOWN_LADDER) ? 1 : (a == TG_INTERACT) ? 4 : (a <= TG_DOWN_RIGHT) ? 2 : 3;
+                bucket = cls * 12 + 11 - min(estimate_ticks(e, L, a, tcx) / 10, 11);
+            }
+            info[el] = pack_info(ran, err, tcx, bucket, a);
+            atomicAdd(&hist[bucket], 1);
+        }
+    }
+    __syncthreads();
+    phase_stamp(B, 3);
+    // ---- phase 2: exclusive scan of the 64 class counts (warp 0), then scatter the runnable envs; count the
+    // runnable envs of every 32-env index chunk (phase 4 finishes a chunk once all of them have run) ----
+    if (tid < 32) scan64(hist, lane);
     __syncthreads();
     for (int el = tid; el < count; el += STEP_THREADS) {
-        const int pos = atomicAdd(&hist[(info[el] >> 8) & 63], 1);
-        perm[pos] = (uint16_t)el;
+        const uint32_t inf = info[el];
+        if (inf & 1u) { perm[atomicAdd(&hist[(inf >> 8) & 63], 1)] = (uint16_t)el; atomicAdd(&pending[el >> 5], 1); }
     }
-    __syncthreads();
-
-    // ---- phase 3: execute, longest chunks first -------------------------------
-    int st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int n_run = hist[NBUCKET - 1];                    // exclusive scan: start of bucket 63 (not runnable) = runnable envs
     const int nchunks = (count + 31) >> 5;
+    __syncthreads();
+    for (int c = tid; c < nchunks; c += STEP_THREADS)
+        if (pending[c] == 0) ready[atomicAdd(&ready_tail, 1)] = (uint16_t)c;
+    __syncthreads();                                        // phase 3 decrements `pending`: only after the scan above
+    phase_stamp(B, 4);
+
+    // ---- phase 3: the runnable envs, 32-env chunks in class order from a shared counter (longest first).  A lane
+    // runs its env's option to termination and puts the state back; info[el] becomes: bits 0-12 ticks, bit 13 env
+    // newly flagged, bits 14-17 option id, bit 18 "ran", bits 19-31 uniforms drawn.  The env that completes an index
+    // chunk hands the chunk to phase 4 through the `ready` queue.
+    const int nrc = (n_run + 31) >> 5;
     for (;;) {
         int c = 0;
         if (lane == 0) c = atomicAdd(&next_chunk, 1);
         c = __shfl_sync(0xFFFFFFFFu, c, 0);
-        if (c >= nchunks) break;
+        if (c >= nrc) break;
         const int j = c * 32 + lane;
-        if (j < count) {
+        if (j < n_run) {
             const int el = perm[j];
             const uint32_t inf = info[el];
             const int64_t i = base + el;
@@ -146,32 +232,103 @@ tg_step_kernel(BatchView B, const int32_t *__restrict__ actions, float *__restri
             Env<NI> e;
             uint4 acct;
             load_env(e, B, i, acct);
-            const int a = actions[i];
+            const int a = (int)((inf >> 14) & 15u);
             const uint32_t err0 = e.flags & (1u << F_ERROR);
-            int n = 0;
-            if (inf & 1u) n = run_option_to_end<TAPE>(e, L, a, (int)((inf >> 2) & 63u) - 8);
-            else if (inf & 2u) e.flags |= 1u << F_ERROR;
+            const int n = run_option_to_end<TAPE>(e, L, a, (int)((inf >> 2) & 63u) - 8);
+            store_env(e, B, i, acct);
+            const uint32_t newerr = ((e.flags & (1u << F_ERROR)) && !err0) ? 1u : 0u;
+            info[el] = (uint32_t)n | (newerr << 13) | ((uint32_t)a << 14) | (1u << 18) | ((e.draws - e.d0) << 19);
+            __threadfence_block();                                          // state + info before the hand-over
+            if (atomicSub(&pending[el >> 5], 1) == 1) ready[atomicAdd(&ready_tail, 1)] = (uint16_t)(el >> 5);
+        }
+    }
+    phase_stamp(B, 5);
+
+    // ---- phase 4: every env, one complete 32-env index chunk at a time as chunks become ready (no barrier: a warp
+    // comes here as soon as the runnable chunks are handed out, and every env it may wait for is already running):
+    // reward / done / time-limit / auto-reset (rare: out of line, through memory) / outputs.  Loads and stores are
+    // contiguous; observation rows are built in shared memory and leave with full-line stores.
+    uint32_t st_cnt = 0;                                    // errors | episodes << 8 | successes << 16 | ran << 24
+    int st_ticks = 0, st_ret = 0, st_epsteps = 0;
+    const int od = B.obs_dim;
+    float *stage = reinterpret_cast<float *>(smem_raw + (((size_t)B.n_levels * sizeof(LevelBlob) + 15) & ~(size_t)15))
+                   + (size_t)(tid >> 5) * 32 * od;                             // this warp's [32][obs_dim] rows
+    const bool vec_ok = obs && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0);
+    for (;;) {
+        int c = -1;
+        if (lane == 0) {
+            const int pos = atomicAdd(&ready_head, 1);
+            if (pos < nchunks) {
+                volatile uint16_t *rq = ready;
+                while ((c = rq[pos]) == 0xFFFF) __nanosleep(64);
+            }
+        }
+        c = __shfl_sync(0xFFFFFFFFu, c, 0);
+        if (c < 0) break;
+        __threadfence_block();
+        const int el0 = c * 32, el = el0 + lane;
+        const int rows = min(32, count - el0);
+        if (el < count) {
+            const uint32_t inf = info[el];
+            const int64_t i = base + el;
+            const int lid = B.level_id ? B.level_id[i] : 0;
+            const LevelBlob &L = levels[lid];
+            Env<NI> e;
+            uint4 cv = B.core[i];
+            uint4 acct = B.acct[i];
+            load_core(e, B, i, cv);
+            e.angles = B.angles + i; e.n = B.n;
+            const bool ran = (inf >> 18) & 1u;
+            const int a = (int)((inf >> 14) & 15u);
+            const int n = ran ? (int)(inf & 0x1FFFu) : 0;
+            if (ran) st_cnt += ((inf >> 13) & 1u) + (1u << 24);
+            else if ((inf & 2u) && !(e.flags & (1u << F_ERROR))) {        // the reference would raise (target None)
+                e.flags |= 1u << F_ERROR; st_cnt += 1u;
+                cv.y = e.flags; B.core[i] = cv;
+            }
             const int r = n ? -n - ((a >= TG_JUMP_LEFT) ? 4 : 0) : 0;       // impl:15-16: -1 per tick, JUMP tick -5
             acct.y = (uint32_t)((int)acct.y + r);
             acct.z += 1u;
+            st_ticks += n;
             const bool term = is_done(e, L);
             const bool trunc = B.max_steps > 0 && acct.z >= (uint32_t)B.max_steps;
             const int d = (term ? TG_DONE_TERMINATED : 0) | (trunc ? TG_DONE_TRUNCATED : 0);
-            st[ST_TICKS] += n; st[ST_RAN] += n > 0; st[ST_STEPS] += 1;
-            st[ST_ERRORS] += ((e.flags & (1u << F_ERROR)) && !err0) ? 1 : 0;
             if (d) {
-                st[ST_EPISODES] += 1; st[ST_SUCCESS] += term; st[ST_RETURN] += (int)acct.y; st[ST_EPSTEPS] += (int)acct.z;
-                if (B.auto_reset) { reset_env<TAPE>(e, L); acct.y = 0; acct.z = 0; }
+                st_cnt += (1u << 8) + (term ? 1u << 16 : 0u); st_ret += (int)acct.y; st_epsteps += (int)acct.z;
+                if (B.auto_reset) {
+                    acct.y = 0; acct.z = 0;
+                    B.acct[i] = acct;
+                    reset_in_memory<TAPE, NI>(B, &L, i, ran ? inf >> 19 : 0u);
+                    acct = B.acct[i];
+                    load_core(e, B, i);
+                }
             }
-            store_env(e, B, i, acct);
-            if (obs) write_obs(e, L, obs + i * B.obs_dim, B.obs_dim);
+            B.acct[i] = acct;
+            if (obs) write_obs(e, L, B.obs_lut + (size_t)lid * 2 * OBS_LUT_N, stage + lane * od, od);
             if (reward) reward[i] = (float)r;
             if (done_out) done_out[i] = (uint8_t)d;
             if (ran_out) ran_out[i] = (uint8_t)(n > 0);
             if (avail_out) avail_out[i] = (uint16_t)available_bits(e, L);
         }
+        if (obs) {
+            __syncwarp();
+            float *dst = obs + (base + el0) * od;
+            const int nf = rows * od;
+            if (vec_ok && (nf & 3) == 0) {
+                for (int q = lane; q < (nf >> 2); q += 32) reinterpret_cast<float4 *>(dst)[q] = reinterpret_cast<const float4 *>(stage)[q];
+            } else {
+                for (int q = lane; q < nf; q += 32) dst[q] = stage[q];
+            }
+            __syncwarp();
+        }
     }
+    phase_stamp(B, 6);
+    int st[8];
+    st[ST_EPISODES] = (st_cnt >> 8) & 255; st[ST_SUCCESS] = (st_cnt >> 16) & 255; st[ST_RETURN] = st_ret; st[ST_EPSTEPS] = st_epsteps;
+    st[ST_TICKS] = st_ticks; st[ST_RAN] = st_cnt >> 24; st[ST_ERRORS] = st_cnt & 255;
+    st[ST_STEPS] = (tid == 0) ? count : 0;                  // every env of the tile takes exactly one gym step
     stats_accumulate(sh_stats, B.stats, st);
+    phase_stamp(B, 7);
 }
 
 template <bool TAPE, int NI>
@@ -193,7 +350,7 @@ tg_reset_kernel(BatchView B, const uint8_t *__restrict__ mask, float *__restrict
         acct.y = 0; acct.z = 0;
         store_env(e, B, i, acct);
     }
-    if (obs) write_obs(e, L, obs + i * B.obs_dim, B.obs_dim);
+    if (obs) write_obs(e, L, B.obs_lut + (size_t)(B.level_id ? B.level_id[i] : 0) * 2 * OBS_LUT_N, obs + i * B.obs_dim, B.obs_dim);
 }
 
 template <int NI>
@@ -250,7 +407,7 @@ tg_primitive_kernel(BatchView B, const int32_t *__restrict__ actions, float *__r
             if (B.auto_reset) { reset_env<TAPE>(e, L); acct.y = 0; acct.z = 0; }
         }
         store_env(e, B, i, acct);
-        if (obs) write_obs(e, L, obs + i * B.obs_dim, B.obs_dim);
+        if (obs) write_obs(e, L, B.obs_lut + (size_t)(B.level_id ? B.level_id[i] : 0) * 2 * OBS_LUT_N, obs + i * B.obs_dim, B.obs_dim);
         if (reward) reward[i] = (float)r;
         if (done_out) done_out[i] = (uint8_t)d;
     }
@@ -350,36 +507,60 @@ __global__ void tg_set_state_kernel(BatchView B, tg_state_view v) {
 // ---------------------------------------------------------------------------
 static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 static inline size_t level_smem(const BatchView &B) { return (size_t)B.n_levels * sizeof(LevelBlob); }
+// step kernel: level blobs + one [32][obs_dim] float staging area per warp for the coalesced observation rows
+static inline size_t step_smem(const BatchView &B) {
+    return ((level_smem(B) + 15) & ~(size_t)15) + (size_t)(STEP_THREADS / 32) * 32 * B.obs_dim * sizeof(float);
+}
 
 template <bool TAPE, int NI, int TILE>
-static cudaError_t step_tile(const BatchView &B, const int32_t *a, float *obs, float *rew, uint8_t *done,
+static cudaError_t step_tile(const BatchView &B, int tile, const int32_t *a, float *obs, float *rew, uint8_t *done,
                              uint8_t *ran, uint16_t *avail, cudaStream_t s) {
-    tg_step_kernel<TAPE, NI, TILE><<<grid_for(B.r_count, TILE), STEP_THREADS, level_smem(B), s>>>(B, a, obs, rew, done, ran, avail);
+    const size_t smem = step_smem(B);
+    if (smem > 32 * 1024) {      // many layouts with long observations: opt in beyond the default 48 KB (static + dynamic)
+        static size_t allowed = 0;
+        if (smem > allowed) {
+            cudaError_t r = cudaFuncSetAttribute(tg_step_kernel<TAPE, NI, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (r != cudaSuccess) return r;
+            allowed = smem;
+        }
+    }
+    tg_step_kernel<TAPE, NI, TILE><<<grid_for(B.r_count, tile), STEP_THREADS, step_smem(B), s>>>(B, tile, a, obs, rew, done, ran, avail);
     return cudaGetLastError();
 }
 
 template <bool TAPE, int NI>
 static cudaError_t step_impl(const BatchView &B, int tile, const int32_t *a, float *obs, float *rew, uint8_t *done,
                              uint8_t *ran, uint16_t *avail, cudaStream_t s) {
-    switch (tile) {
-    case 256:  return step_tile<TAPE, NI, 256>(B, a, obs, rew, done, ran, avail, s);
-    case 512:  return step_tile<TAPE, NI, 512>(B, a, obs, rew, done, ran, avail, s);
-    case 1024: return step_tile<TAPE, NI, 1024>(B, a, obs, rew, done, ran, avail, s);
-    case 4096: return step_tile<TAPE, NI, 4096>(B, a, obs, rew, done, ran, avail, s);
-    default:   return step_tile<TAPE, NI, 2048>(B, a, obs, rew, done, ran, avail, s);
-    }
+    if (tile <= 256) return step_tile<TAPE, NI, 256>(B, tile, a, obs, rew, done, ran, avail, s);     // capacity of the shared arrays
+    if (tile <= 512) return step_tile<TAPE, NI, 512>(B, tile, a, obs, rew, done, ran, avail, s);
+    if (tile <= 1024) return step_tile<TAPE, NI, 1024>(B, tile, a, obs, rew, done, ran, avail, s);
+    if (tile <= 2048) return step_tile<TAPE, NI, 2048>(B, tile, a, obs, rew, done, ran, avail, s);
+    return step_tile<TAPE, NI, 4096>(B, tile, a, obs, rew, done, ran, avail, s);
 }
 
-// Tile size: large tiles sort better (more runnable envs per tile -> fuller warps); small tiles give
-// more CTAs.  Aim for >= 4 CTAs per SM (148 SMs) when the batch allows it.  TG_STEP_TILE overrides.
+// Tile size: large tiles sort better (more runnable envs per tile -> fuller warps); small tiles give more
+// CTAs.  The grid is sized in whole "slots": 148 SMs x 4 resident CTAs = 592 CTAs run at once, so the tile is
+// n / (592 * waves) rounded up -- with 2048-env tiles a 1,048,576-env step had 512 CTAs, 68 SMs held four of
+// them and 80 SMs three.  Smaller batches aim for two, then one CTA per SM slot.  TG_STEP_TILE overrides.
 int pick_step_tile(int64_t n) {
-    static int forced = -1;
+    static int forced = -1, slots = 0;
     if (forced < 0) { const char *v = getenv("TG_STEP_TILE"); forced = v ? atoi(v) : 0; }
-    if (forced == 256 || forced == 512 || forced == 1024 || forced == 2048 || forced == 4096) return forced;
-    if (n >= (int64_t)2048 * 296) return 2048;      // measured at 1,048,576 envs: 256/512/1024/2048 -> 1.25/1.82/2.36/3.09 G steps/s
-    if (n >= (int64_t)1024 * 296) return 1024;
-    if (n >= (int64_t)512 * 296) return 512;
-    return 256;
+    if (forced >= 32 && forced <= 4096) return forced;
+    if (!slots) {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        slots = sms * TG_STEP_MIN_BLOCKS;
+    }
+    const int64_t cap = 2048;
+    int64_t ctas;
+    if (n >= (int64_t)slots * 512) ctas = (n + slots * cap - 1) / (slots * cap) * slots;      // whole waves of full occupancy
+    else if (n >= (int64_t)slots * 128) ctas = slots / 2;                                      // two CTAs per SM
+    else ctas = (n + 255) / 256;
+    int64_t tile = (n + ctas - 1) / ctas;
+    tile = (tile + 3) / 4 * 4;
+    if (tile < 32) tile = 32;
+    if (tile > 4096) tile = 4096;
+    return (int)tile;
 }
 
 cudaError_t launch_step(const BatchView &B, int ni, const int32_t *a, float *obs, float *rew, uint8_t *done,

@@ -53,6 +53,8 @@ struct alignas(16) LevelBlob {
     uint8_t trig_dst[TG_MAX_TRIGGERS];
     float inv_w, inv_h;                  // unused by parity paths (obs divides in double)
     uint32_t pad_[2];
+    // observation program (impl:368-378): obs slot k = OP_* << 4 | index (handle / bolt / item number)
+    uint8_t obs_prog[32];
     // row bit masks over the padded columns (bit = column index + PAD), door cells cleared:
     uint32_t row_nonopen[TSTRIDE];       // WALL or LADDER (anything but OPEN)          -> can_fall, up_clear
     uint32_t row_solid[TSTRIDE];         // WALL                                          -> can_go_left/right
@@ -62,6 +64,11 @@ struct alignas(16) LevelBlob {
     uint32_t door_lut[TG_MAX_DOORS][64]; // [rows with doors][closed-door bits] -> column bits of the closed doors of the row
 };
 static_assert(sizeof(LevelBlob) % 16 == 0, "LevelBlob must be a multiple of 16 bytes");
+
+// observation program opcodes and the quotient tables behind OP_PX .. OP_IY: lut[0][v + S] = float(v / W) and
+// lut[1][v + S] = float(v / H) for v in [-S, OBS_LUT_N - S), one pair of tables per level (BatchView::obs_lut)
+enum : int { OP_PX = 0, OP_PY, OP_ANGLE, OP_BOLT, OP_IX, OP_IY, OP_ZERO };
+constexpr int OBS_LUT_N = TG_MAX_GRID * TG_CELL_PX + TG_CELL_PX;
 
 // stats vector slots (tg_stats)
 enum : int { ST_EPISODES = 0, ST_SUCCESS, ST_RETURN, ST_EPSTEPS, ST_TICKS, ST_RAN, ST_STEPS, ST_ERRORS };
@@ -85,6 +92,8 @@ struct BatchView {
     const double *tape;   // parity mode, or NULL
     const int64_t *tape_off;
     unsigned long long *stats;   // [8]
+    const float *obs_lut;        // [n_levels][2][OBS_LUT_N]
+    unsigned long long *phase_ts; // debug: [grid][8] globaltimer stamps of the step kernel's phases, or NULL
 };
 
 }  // namespace tg

@@ -185,6 +185,11 @@ int tg_set_draw_tape(tg_env *env, const double *tape, const int64_t *offsets, vo
 int tg_stats(tg_env *env, int64_t *out8, void *stream);
 int tg_stats_clear(tg_env *env, void *stream);
 
+/* Debug instrumentation: DEV uint64[grid][8] (or NULL to switch off).  When set, thread 0 of every step-kernel CTA
+ * writes %globaltimer (ns) at its phase boundaries: start, levels staged, option sort, classified, class sort,
+ * options executed, outputs written, statistics done.  Used by tools/bench_phases.py; not part of the reference surface. */
+int tg_debug_phase_buffer(tg_env *env, uint64_t *stamps);
+
 /* how many kernels this library has launched on behalf of `env` (bench bookkeeping) */
 int64_t tg_launch_count(const tg_env *env);
 
