@@ -61,9 +61,9 @@ __device__ __forceinline__ void phase_stamp(const BatchView &B, int slot) {
 }
 
 // info word per env of the tile: bit 0 runnable, bit 1 reference-would-raise, bits 2-7 target column + 8,
-// bits 8-13 bucket, bits 14-17 option id (9 = not an option id)
+// bits 8-13 bucket, bits 14-17 option id (9 = not an option id), bit 18 runnable (kept by the later format)
 __device__ __forceinline__ uint32_t pack_info(bool ran, bool err, int tcx, int bucket, int a) {
-    return (ran ? 1u : 0u) | (err ? 2u : 0u) | ((uint32_t)((tcx + 8) & 63) << 2) | ((uint32_t)bucket << 8) | ((uint32_t)a << 14);
+    return (ran ? 1u | (1u << 18) : 0u) | (err ? 2u : 0u) | ((uint32_t)((tcx + 8) & 63) << 2) | ((uint32_t)bucket << 8) | ((uint32_t)a << 14);
 }
 
 // Reset of an env whose option did not run (time limit): out of line and through memory, so that the common
@@ -118,9 +118,8 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, const int32_t *__r
     __shared__ uint64_t bar;
     __shared__ int sh_stats[8];
     __shared__ int hist[NBUCKET];
-    __shared__ int next_chunk, ready_head, ready_tail;
-    __shared__ int pending[TILE / 32];          // runnable envs of each 32-env index chunk that have not finished yet
-    __shared__ uint16_t ready[TILE / 32];       // queue of complete index chunks (0xFFFF = slot not filled yet)
+    __shared__ int next_chunk;
+    __shared__ uint8_t ckey[TILE / 32], order[TILE / 32];   // length class of each runnable chunk; chunks longest first
     __shared__ uint32_t info[TILE];
     __shared__ uint16_t perm0[TILE];
     __shared__ uint16_t perm[TILE];
@@ -128,8 +127,7 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, const int32_t *__r
     phase_stamp(B, 0);
     if (tid < 8) sh_stats[tid] = 0;
     if (tid < NBUCKET) hist[tid] = 0;
-    if (tid == 0) { next_chunk = 0; ready_head = 0; ready_tail = 0; }
-    if (tid < TILE / 32) { pending[tid] = 0; ready[tid] = 0xFFFF; }
+    if (tid == 0) next_chunk = 0;
     stage_levels(levels, B.levels, B.n_levels, &bar);      // contains a __syncthreads()
     phase_stamp(B, 1);
 
@@ -197,78 +195,72 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, const int32_t *__r
     }
     __syncthreads();
     phase_stamp(B, 3);
-    // ---- phase 2: exclusive scan of the 64 class counts (warp 0), then scatter the runnable envs; count the
-    // runnable envs of every 32-env index chunk (phase 4 finishes a chunk once all of them have run) ----
+    // ---- phase 2: exclusive scan of the 64 class counts (warp 0), scatter the runnable envs, then order their
+    // 32-env chunks longest first across classes (a chunk's first env is its longest: length is the minor key) ----
     if (tid < 32) scan64(hist, lane);
     __syncthreads();
     for (int el = tid; el < count; el += STEP_THREADS) {
         const uint32_t inf = info[el];
-        if (inf & 1u) { perm[atomicAdd(&hist[(inf >> 8) & 63], 1)] = (uint16_t)el; atomicAdd(&pending[el >> 5], 1); }
+        if (inf & 1u) perm[atomicAdd(&hist[(inf >> 8) & 63], 1)] = (uint16_t)el;
     }
     const int n_run = hist[NBUCKET - 1];                    // exclusive scan: start of bucket 63 (not runnable) = runnable envs
-    const int nchunks = (count + 31) >> 5;
-    __syncthreads();
-    for (int c = tid; c < nchunks; c += STEP_THREADS)
-        if (pending[c] == 0) ready[atomicAdd(&ready_tail, 1)] = (uint16_t)c;
-    __syncthreads();                                        // phase 3 decrements `pending`: only after the scan above
-    phase_stamp(B, 4);
-
-    // ---- phase 3: the runnable envs, 32-env chunks in class order from a shared counter (longest first).  A lane
-    // runs its env's option to termination and puts the state back; info[el] becomes: bits 0-12 ticks, bit 13 env
-    // newly flagged, bits 14-17 option id, bit 18 "ran", bits 19-31 uniforms drawn.  The env that completes an index
-    // chunk hands the chunk to phase 4 through the `ready` queue.
     const int nrc = (n_run + 31) >> 5;
-    for (;;) {
-        int c = 0;
-        if (lane == 0) c = atomicAdd(&next_chunk, 1);
-        c = __shfl_sync(0xFFFFFFFFu, c, 0);
-        if (c >= nrc) break;
-        const int j = c * 32 + lane;
-        if (j < n_run) {
-            const int el = perm[j];
-            const uint32_t inf = info[el];
-            const int64_t i = base + el;
-            const LevelBlob &L = levels[B.level_id ? B.level_id[i] : 0];
-            Env<NI> e;
-            uint4 acct;
-            load_env(e, B, i, acct);
-            const int a = (int)((inf >> 14) & 15u);
-            const uint32_t err0 = e.flags & (1u << F_ERROR);
-            const int n = run_option_to_end<TAPE>(e, L, a, (int)((inf >> 2) & 63u) - 8);
-            store_env(e, B, i, acct);
-            const uint32_t newerr = ((e.flags & (1u << F_ERROR)) && !err0) ? 1u : 0u;
-            info[el] = (uint32_t)n | (newerr << 13) | ((uint32_t)a << 14) | (1u << 18) | ((e.draws - e.d0) << 19);
-            __threadfence_block();                                          // state + info before the hand-over
-            if (atomicSub(&pending[el >> 5], 1) == 1) ready[atomicAdd(&ready_tail, 1)] = (uint16_t)(el >> 5);
+    __syncthreads();
+    if (tid < 32) {
+        for (int c = lane; c < nrc; c += 32) ckey[c] = (uint8_t)(11 - ((info[perm[c * 32]] >> 8) & 63u) % 12u);
+        __syncwarp();
+        for (int c = lane; c < nrc; c += 32) {
+            const int k = ckey[c];
+            int r = 0;
+            for (int j = 0; j < nrc; j++) { const int kj = ckey[j]; r += (kj > k || (kj == k && j < c)) ? 1 : 0; }
+            order[r] = (uint8_t)c;
         }
     }
-    phase_stamp(B, 5);
+    __syncthreads();
+    phase_stamp(B, 4);
 
-    // ---- phase 4: every env, one complete 32-env index chunk at a time as chunks become ready (no barrier: a warp
-    // comes here as soon as the runnable chunks are handed out, and every env it may wait for is already running):
-    // reward / done / time-limit / auto-reset (rare: out of line, through memory) / outputs.  Loads and stores are
-    // contiguous; observation rows are built in shared memory and leave with full-line stores.
     uint32_t st_cnt = 0;                                    // errors | episodes << 8 | successes << 16 | ran << 24
     int st_ticks = 0, st_ret = 0, st_epsteps = 0;
     const int od = B.obs_dim;
     float *stage = reinterpret_cast<float *>(smem_raw + (((size_t)B.n_levels * sizeof(LevelBlob) + 15) & ~(size_t)15))
                    + (size_t)(tid >> 5) * 32 * od;                             // this warp's [32][obs_dim] rows
     const bool vec_ok = obs && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0);
+
+    // ---- phase 3: one queue of 32-env chunks from a shared counter.  First the runnable envs (class-sorted chunks,
+    // longest first): a lane runs its env's option to termination and puts the state back; info[el] becomes bits
+    // 0-12 ticks, bit 13 env newly flagged, bits 14-17 option id, bit 18 set, bits 19-31 uniforms drawn.  Then every
+    // index-order chunk, for the envs whose option did not run (so this work overlaps the long options above):
+    // time-limit / auto-reset (rare: out of line, through memory) / outputs with contiguous loads and stores.
+    // Observation rows are built in shared memory and leave with full-line stores; the rows of the envs that ran
+    // are rewritten by phase 5.
+    const int nchunks = nrc + ((count + 31) >> 5);
     for (;;) {
-        int c = -1;
-        if (lane == 0) {
-            const int pos = atomicAdd(&ready_head, 1);
-            if (pos < nchunks) {
-                volatile uint16_t *rq = ready;
-                while ((c = rq[pos]) == 0xFFFF) __nanosleep(64);
+        int q = 0;
+        if (lane == 0) q = atomicAdd(&next_chunk, 1);
+        q = __shfl_sync(0xFFFFFFFFu, q, 0);
+        if (q >= nchunks) break;
+        if (q < nrc) {
+            const int j = order[q] * 32 + lane;
+            if (j < n_run) {
+                const int el = perm[j];
+                const uint32_t inf = info[el];
+                const int64_t i = base + el;
+                const LevelBlob &L = levels[B.level_id ? B.level_id[i] : 0];
+                Env<NI> e;
+                uint4 acct;
+                load_env(e, B, i, acct);
+                const int a = (int)((inf >> 14) & 15u);
+                const uint32_t err0 = e.flags & (1u << F_ERROR);
+                const int n = run_option_to_end<TAPE>(e, L, a, (int)((inf >> 2) & 63u) - 8);
+                store_env(e, B, i, acct);
+                const uint32_t newerr = ((e.flags & (1u << F_ERROR)) && !err0) ? 1u : 0u;
+                info[el] = (uint32_t)n | (newerr << 13) | ((uint32_t)a << 14) | (1u << 18) | ((e.draws - e.d0) << 19);
             }
+            continue;
         }
-        c = __shfl_sync(0xFFFFFFFFu, c, 0);
-        if (c < 0) break;
-        __threadfence_block();
-        const int el0 = c * 32, el = el0 + lane;
+        const int el0 = (q - nrc) * 32, el = el0 + lane;
         const int rows = min(32, count - el0);
-        if (el < count) {
+        if (el < count && !((info[el] >> 18) & 1u)) {
             const uint32_t inf = info[el];
             const int64_t i = base + el;
             const int lid = B.level_id ? B.level_id[i] : 0;
@@ -278,18 +270,11 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, const int32_t *__r
             uint4 acct = B.acct[i];
             load_core(e, B, i, cv);
             e.angles = B.angles + i; e.n = B.n;
-            const bool ran = (inf >> 18) & 1u;
-            const int a = (int)((inf >> 14) & 15u);
-            const int n = ran ? (int)(inf & 0x1FFFu) : 0;
-            if (ran) st_cnt += ((inf >> 13) & 1u) + (1u << 24);
-            else if ((inf & 2u) && !(e.flags & (1u << F_ERROR))) {        // the reference would raise (target None)
+            if ((inf & 2u) && !(e.flags & (1u << F_ERROR))) {                // the reference would raise (target None)
                 e.flags |= 1u << F_ERROR; st_cnt += 1u;
                 cv.y = e.flags; B.core[i] = cv;
             }
-            const int r = n ? -n - ((a >= TG_JUMP_LEFT) ? 4 : 0) : 0;       // impl:15-16: -1 per tick, JUMP tick -5
-            acct.y = (uint32_t)((int)acct.y + r);
             acct.z += 1u;
-            st_ticks += n;
             const bool term = is_done(e, L);
             const bool trunc = B.max_steps > 0 && acct.z >= (uint32_t)B.max_steps;
             const int d = (term ? TG_DONE_TERMINATED : 0) | (trunc ? TG_DONE_TRUNCATED : 0);
@@ -298,16 +283,16 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, const int32_t *__r
                 if (B.auto_reset) {
                     acct.y = 0; acct.z = 0;
                     B.acct[i] = acct;
-                    reset_in_memory<TAPE, NI>(B, &L, i, ran ? inf >> 19 : 0u);
+                    reset_in_memory<TAPE, NI>(B, &L, i, 0u);
                     acct = B.acct[i];
                     load_core(e, B, i);
                 }
             }
             B.acct[i] = acct;
             if (obs) write_obs(e, L, B.obs_lut + (size_t)lid * 2 * OBS_LUT_N, stage + lane * od, od);
-            if (reward) reward[i] = (float)r;
+            if (reward) reward[i] = 0.0f;
             if (done_out) done_out[i] = (uint8_t)d;
-            if (ran_out) ran_out[i] = (uint8_t)(n > 0);
+            if (ran_out) ran_out[i] = (uint8_t)0;
             if (avail_out) avail_out[i] = (uint16_t)available_bits(e, L);
         }
         if (obs) {
@@ -315,12 +300,53 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, const int32_t *__r
             float *dst = obs + (base + el0) * od;
             const int nf = rows * od;
             if (vec_ok && (nf & 3) == 0) {
-                for (int q = lane; q < (nf >> 2); q += 32) reinterpret_cast<float4 *>(dst)[q] = reinterpret_cast<const float4 *>(stage)[q];
+                for (int k = lane; k < (nf >> 2); k += 32) reinterpret_cast<float4 *>(dst)[k] = reinterpret_cast<const float4 *>(stage)[k];
             } else {
-                for (int q = lane; q < nf; q += 32) dst[q] = stage[q];
+                for (int k = lane; k < nf; k += 32) dst[k] = stage[k];
             }
             __syncwarp();
         }
+    }
+    __syncthreads();      // every option has run; the rows written above are ordered before the ones written below
+    phase_stamp(B, 5);
+
+    // ---- phase 5: the envs whose option ran: reward / done / time-limit / auto-reset / outputs ----
+    for (int j = tid; j < n_run; j += STEP_THREADS) {
+        const int el = perm[j];
+        const uint32_t inf = info[el];
+        const int64_t i = base + el;
+        const int lid = B.level_id ? B.level_id[i] : 0;
+        const LevelBlob &L = levels[lid];
+        Env<NI> e;
+        uint4 acct = B.acct[i];
+        load_core(e, B, i);
+        e.angles = B.angles + i; e.n = B.n;
+        const int a = (int)((inf >> 14) & 15u);
+        const int n = (int)(inf & 0x1FFFu);
+        st_cnt += ((inf >> 13) & 1u) + (1u << 24);
+        st_ticks += n;
+        const int r = -n - ((a >= TG_JUMP_LEFT) ? 4 : 0);                    // impl:15-16: -1 per tick, JUMP tick -5
+        acct.y = (uint32_t)((int)acct.y + r);
+        acct.z += 1u;
+        const bool term = is_done(e, L);
+        const bool trunc = B.max_steps > 0 && acct.z >= (uint32_t)B.max_steps;
+        const int d = (term ? TG_DONE_TERMINATED : 0) | (trunc ? TG_DONE_TRUNCATED : 0);
+        if (d) {
+            st_cnt += (1u << 8) + (term ? 1u << 16 : 0u); st_ret += (int)acct.y; st_epsteps += (int)acct.z;
+            if (B.auto_reset) {
+                acct.y = 0; acct.z = 0;
+                B.acct[i] = acct;
+                reset_in_memory<TAPE, NI>(B, &L, i, inf >> 19);
+                acct = B.acct[i];
+                load_core(e, B, i);
+            }
+        }
+        B.acct[i] = acct;
+        if (obs) write_obs(e, L, B.obs_lut + (size_t)lid * 2 * OBS_LUT_N, obs + i * od, od);
+        if (reward) reward[i] = (float)r;
+        if (done_out) done_out[i] = (uint8_t)d;
+        if (ran_out) ran_out[i] = (uint8_t)1;
+        if (avail_out) avail_out[i] = (uint16_t)available_bits(e, L);
     }
     phase_stamp(B, 6);
     int st[8];
