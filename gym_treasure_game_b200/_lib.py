@@ -62,6 +62,10 @@ _SIGNATURES = {
     "tg_step_host": (C.c_int, [C.c_void_p] * 7),
     "tg_available_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tg_render": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "tg_blend": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "tg_background": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "tg_blit_alpha": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                C.c_int32, C.c_int32, C.c_void_p]),
     "tg_get_state": (C.c_int, [C.c_void_p, C.POINTER(TgStateView), C.c_void_p]),
     "tg_set_state": (C.c_int, [C.c_void_p, C.POINTER(TgStateView), C.c_void_p]),
     "tg_primitive_step": (C.c_int, [C.c_void_p] * 6),

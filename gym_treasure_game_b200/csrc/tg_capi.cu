@@ -466,6 +466,40 @@ extern "C" int tg_render(tg_env *env, int64_t first, int64_t count, uint8_t *fra
     return TG_OK;
 }
 
+extern "C" int tg_blend(tg_env *env, int64_t first, int64_t count, int64_t per_surface, uint8_t *surfaces,
+                        int32_t alpha_objs, int32_t alpha_player, void *stream) {
+    if (!env || !surfaces) return fail(TG_ERR_ARG, "null argument");
+    if (!env->has_render) return fail(TG_ERR_STATE, "blend needs tg_level_set_sprites on every level (and equal grid sizes)");
+    if (first < 0 || count < 0 || first + count > env->B.n) return fail(TG_ERR_ARG, "env range outside the batch");
+    if (per_surface < 1 || count % per_surface != 0) return fail(TG_ERR_ARG, "count must be a multiple of per_surface");
+    if (alpha_objs < 0 || alpha_objs > 255 || alpha_player < 0 || alpha_player > 255) return fail(TG_ERR_ARG, "opacities are 0..255");
+    if (reinterpret_cast<uintptr_t>(surfaces) & 15u) return fail(TG_ERR_ARG, "surfaces must be 16-byte aligned");
+    if (count == 0) return TG_OK;
+    DeviceGuard guard(env->device);
+    CU(launch_blend(env->B, env->R, first, count / per_surface, per_surface, surfaces, alpha_objs, alpha_player, (cudaStream_t)stream));
+    env->launches += (count / per_surface + 32767) / 32768;
+    return TG_OK;
+}
+
+extern "C" int tg_background(tg_env *env, int32_t level, uint8_t *frame, void *stream) {
+    if (!env || !frame) return fail(TG_ERR_ARG, "null argument");
+    if (!env->has_render) return fail(TG_ERR_STATE, "no render assets (tg_level_set_sprites)");
+    if (level < 0 || level >= env->n_levels) return fail(TG_ERR_ARG, "level %d outside 0..%d", level, env->n_levels - 1);
+    DeviceGuard guard(env->device);
+    CU(cudaMemcpyAsync(frame, env->R.assets[level].background, (size_t)env->R.frame_w * env->R.frame_h * 3,
+                       cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return TG_OK;
+}
+
+extern "C" int tg_blit_alpha(uint8_t *target, int32_t tw, int32_t th, const uint8_t *source, int32_t sw, int32_t sh,
+                             int32_t channels, int32_t x, int32_t y, int32_t opacity, void *stream) {
+    if (!target || !source) return fail(TG_ERR_ARG, "null argument");
+    if (tw < 1 || th < 1 || sw < 1 || sh < 1 || (channels != 3 && channels != 4)) return fail(TG_ERR_ARG, "bad surface geometry");
+    if (opacity < 0 || opacity > 255) return fail(TG_ERR_ARG, "opacity is 0..255");
+    CU(launch_blit_alpha(target, tw, th, source, sw, sh, channels, x, y, opacity, (cudaStream_t)stream));
+    return TG_OK;
+}
+
 extern "C" int tg_get_state(tg_env *env, const tg_state_view *out, void *stream) {
     if (!env || !out) return fail(TG_ERR_ARG, "null argument");
     DeviceGuard guard(env->device);

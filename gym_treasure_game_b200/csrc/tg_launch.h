@@ -27,6 +27,10 @@ cudaError_t launch_get_state(const BatchView &B, const tg_state_view &v, cudaStr
 cudaError_t launch_set_state(const BatchView &B, const tg_state_view &v, cudaStream_t s);
 cudaError_t launch_render(const BatchView &B, const RenderView &R, int64_t first, int64_t count,
                           uint8_t *frames, cudaStream_t s);
+cudaError_t launch_blend(const BatchView &B, const RenderView &R, int64_t first, int64_t n_surfaces, int64_t per,
+                         uint8_t *surfaces, int alpha_objs, int alpha_player, cudaStream_t s);
+cudaError_t launch_blit_alpha(uint8_t *target, int tw, int th, const uint8_t *source, int sw, int sh, int channels,
+                              int x0, int y0, int opacity, cudaStream_t s);
 cudaError_t render_configure();   // one-time function attributes (dynamic shared memory opt-in)
 
 }  // namespace tg

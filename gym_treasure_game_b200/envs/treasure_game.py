@@ -60,6 +60,7 @@ class TreasureGame(_EnvBase):
         self.action_space = Discrete(len(OPTION_NAMES))          # treasure_game.py:73
         self.observation_space = Box(np.float32(0.0), np.float32(1.0), shape=(self.level.obs_dim,))   # :75
         self.viewer = None
+        self.drawer = None                                        # created by the first render(), treasure_game.py:99-100
         self._actions = torch.zeros(1, dtype=torch.int32, device=self._vec.device)
 
     # -- helpers ---------------------------------------------------------------
@@ -110,13 +111,43 @@ class TreasureGame(_EnvBase):
         return self._state_vector(), r, bool(info["terminated"][0]), {}
 
     def render(self, mode="human"):
-        rgb = self._vec.render("rgb_array")[0].cpu().numpy()
+        if self.drawer is None:
+            self.drawer = _TreasureGameDrawer(self)               # treasure_game.py:99-100
+        rgb = self.drawer.draw_domain().cpu().numpy()
         if mode == "rgb_array":
             return rgb
         raise NotImplementedError("render('human') needs gym's SimpleImageViewer and a display; use mode='rgb_array'")
 
     def close(self):
         self._vec.close()
+
+
+class _TreasureGameDrawer:
+    """The drawer object the reference keeps on ``env.drawer`` (``_treasure_game_drawer.py:37-269``), for one
+    environment: same method names; surfaces are ``(H, W, 3)`` uint8 CUDA tensors instead of pygame Surfaces."""
+
+    def __init__(self, env: "TreasureGame"):
+        self._vec = env._vec
+        self.screen = None
+
+    def draw_domain(self, show_screen=True):                     # drawer.py:136-163
+        self.screen = self._vec.render("rgb_array")[0]
+        return self.screen
+
+    def draw_background_to_surface(self):                        # :165-182
+        return self._vec.draw_background_to_surface()
+
+    def draw_to_surface(self):                                   # :184-196
+        return self._vec.draw_to_surface()[0]
+
+    def blit_alpha(self, target, source, location, opacity):     # :198-205
+        return self._vec.blit_alpha(target, source, location, opacity)
+
+    def blend(self, surf, alpha_objs, alpha_player):             # :207-231
+        return self._vec.blend(surf, alpha_objs, alpha_player, accumulate=True)
+
+    def draw_to_file(self, fname):                               # :233-236
+        self._vec.draw_to_file(fname)
 
 
 class ObservationWrapper(_WrapperBase):

@@ -212,6 +212,51 @@ class VectorTreasureGame:
         check(self._L.tg_render(self._h, first, count, _ptr(out), self._stream()))
         return out
 
+    # ------------------------------------------------------------------ analysis helpers of the drawer
+    def draw_background_to_surface(self, level: int = 0) -> torch.Tensor:
+        """``_TreasureGameDrawer.draw_background_to_surface`` (drawer.py:165-182): the tile layer, (H, W, 3) uint8."""
+        out = torch.empty(self.frame_shape, dtype=torch.uint8, device=self.device)
+        check(self._L.tg_background(self._h, int(level), _ptr(out), self._stream()))
+        return out
+
+    def draw_to_surface(self, first: int = 0, count: Optional[int] = None) -> torch.Tensor:
+        """``_TreasureGameDrawer.draw_to_surface`` (drawer.py:184-196): the pixels of ``draw_domain`` on fresh
+        surfaces, (count, H, W, 3) uint8."""
+        return self.render("rgb_array", first=first, count=count)
+
+    def blend(self, surfaces: torch.Tensor, alpha_objs: float, alpha_player: float, first: int = 0,
+              count: Optional[int] = None, accumulate: bool = False) -> torch.Tensor:
+        """``_TreasureGameDrawer.blend(surf, alpha_objs, alpha_player)`` (drawer.py:207-231), in place on
+        ``surfaces``: with ``accumulate=False`` surface k (``(count, H, W, 3)`` uint8) receives env ``first + k``;
+        with ``accumulate=True`` one surface ``(H, W, 3)`` receives the envs ``first .. first+count-1`` one after
+        the other (a picture of a set of states)."""
+        count = self.num_envs - first if count is None else count
+        want = self.frame_shape if accumulate else (count,) + self.frame_shape
+        if tuple(surfaces.shape) != tuple(want) or surfaces.dtype != torch.uint8 or surfaces.device != self.device \
+                or not surfaces.is_contiguous():
+            raise ValueError("surfaces must be a contiguous uint8 tensor of shape %s on %s" % (want, self.device))
+        ao, ap = int(255 * alpha_objs), int(255 * alpha_player)            # drawer.py:223, :227
+        check(self._L.tg_blend(self._h, first, count, count if accumulate else 1, _ptr(surfaces), ao, ap, self._stream()))
+        return surfaces
+
+    def blit_alpha(self, target: torch.Tensor, source: torch.Tensor, location, opacity: int) -> torch.Tensor:
+        """``_TreasureGameDrawer.blit_alpha(target, source, location, opacity)`` (drawer.py:198-205), in place on
+        ``target`` (H, W, 3) uint8; ``source`` (h, w, 3 | 4) uint8, both on this env's device."""
+        for t in (target, source):
+            if t.dtype != torch.uint8 or t.device != self.device or not t.is_contiguous() or t.dim() != 3:
+                raise ValueError("target and source must be contiguous (h, w, c) uint8 tensors on %s" % self.device)
+        with torch.cuda.device(self.device):
+            check(self._L.tg_blit_alpha(_ptr(target), target.shape[1], target.shape[0], _ptr(source), source.shape[1],
+                                        source.shape[0], source.shape[2], int(location[0]), int(location[1]), int(opacity),
+                                        self._stream()))
+        return target
+
+    def draw_to_file(self, fname: str, index: int = 0) -> None:
+        """``_TreasureGameDrawer.draw_to_file`` (drawer.py:233-236): the frame of env ``index`` as an image file;
+        like ``pygame.image.save`` the format follows the extension (``.png``, ``.bmp``; anything else is PNG)."""
+        from .imageio import save_rgb
+        save_rgb(fname, self.render("rgb_array", first=index, count=1)[0].cpu().numpy())
+
     # ------------------------------------------------------------------ state access / parity hooks
     def get_state(self) -> Dict[str, torch.Tensor]:
         n, d = self.num_envs, self.device

@@ -158,6 +158,25 @@ int tg_available_mask(tg_env *env, uint8_t *mask, void *stream);
  * frames DEV [count][frame_h][frame_w][3] u8 for envs first .. first+count-1. */
 int tg_render(tg_env *env, int64_t first, int64_t count, uint8_t *frames, void *stream);
 
+/* ---- analysis helpers of the drawer (off the gym path; _treasure_game_drawer.py:165-231) ----
+ * _TreasureGameDrawer.blend (:207-231), batched: surface s (s < count / per_surface) receives the envs
+ * first + s*per_surface .. first + (s+1)*per_surface - 1 one after the other, each as blend(surf, alpha_objs,
+ * alpha_player) would: objects except the handle bases on a transparent overlay blended with opacity alpha_objs,
+ * handle bases at full opacity, the hero with opacity alpha_player.  per_surface = 1 is one blend() per env;
+ * per_surface = count accumulates a set of states on one surface (the use the reference's research code makes
+ * of it).  surfaces DEV [count / per_surface][frame_h][frame_w][3] u8, in/out, 16-byte aligned.  Opacities are
+ * the reference's int(255 * alpha), 0..255. */
+int tg_blend(tg_env *env, int64_t first, int64_t count, int64_t per_surface, uint8_t *surfaces,
+             int32_t alpha_objs, int32_t alpha_player, void *stream);
+/* _TreasureGameDrawer.draw_background_to_surface (:165-182): the tile layer of a level of the batch.
+ * frame DEV [frame_h][frame_w][3] u8.  (draw_to_surface :184-196 has the pixels of tg_render.) */
+int tg_background(tg_env *env, int32_t level, uint8_t *frame, void *stream);
+/* _TreasureGameDrawer.blit_alpha (:198-205): source (RGB or RGBA, channels = 3 | 4) is blended over the region of
+ * target at (x, y) and the result is put back with per-surface opacity.  target DEV [th][tw][3] u8 in/out,
+ * source DEV [sh][sw][channels] u8; clipped to the target.  No tg_env: runs on the current device. */
+int tg_blit_alpha(uint8_t *target, int32_t tw, int32_t th, const uint8_t *source, int32_t sw, int32_t sh,
+                  int32_t channels, int32_t x, int32_t y, int32_t opacity, void *stream);
+
 /* State save / restore on the SoA (test hook; superset of impl:368-378 / :447-481). */
 int tg_get_state(tg_env *env, const tg_state_view *out, void *stream);
 int tg_set_state(tg_env *env, const tg_state_view *in, void *stream);

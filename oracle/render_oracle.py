@@ -219,3 +219,140 @@ def render_frame(level_text, snap, bg=None):
         hero = hero[:, ::-1]                                     # transform.flip(img, True, False), :160
     _blit(screen, hero, snap["px"] - S / 2, snap["py"])          # :157-161
     return screen
+
+
+# ---------------------------------------------------------------------------------------------------
+# Analysis helpers of the drawer: draw_background_to_surface (drawer.py:165-182),
+# draw_to_surface (:184-196), blit_alpha (:198-205), blend (:207-231).  UNPINNED like the rest of this
+# file; the pygame 1.9.6 / SDL 1.2 semantics restated here are:
+#   * Surface((w, h), SRCALPHA, 32) starts as transparent black; draw.line / draw.circle store the mapped
+#     colour (alpha 255) without blending;
+#   * blit of a per-pixel-alpha sprite onto a SRCALPHA surface = pygame's own alphablit_alpha (ALPHA_BLEND):
+#     dA == 0 copies the source pixel, else d = ((d << 8) + (s - d) * sA + s) >> 8 per colour channel and
+#     dA = sA + dA - sA * dA / 255;
+#   * blit of a SRCALPHA surface onto an opaque one = the SDL per-pixel-alpha blit of _blit above;
+#   * set_alpha(a) on an opaque surface + blit onto an opaque surface = SDL per-surface alpha:
+#     a == 255 copies, a == 128 averages ((s & 0xfe) + (d & 0xfe) >> 1) + (s & d & 1), else
+#     d + (((s - d) * a) >> 8) per channel.
+# ---------------------------------------------------------------------------------------------------
+def draw_background_to_surface(tiles):
+    """drawer.py:165-182 -- the tile layer on a fresh surface."""
+    return background(tiles)
+
+
+def draw_to_surface(level_text, snap):
+    """drawer.py:184-196 -- same pixels as draw_domain, on a fresh surface."""
+    return render_frame(level_text, snap)
+
+
+def _surface_alpha_px(s, d, a):
+    """SDL 1.2 per-surface alpha, one channel."""
+    if a == 255:
+        return s
+    if a == 128:
+        return (((s & 0xFE) + (d & 0xFE)) >> 1) + (s & d & 1)
+    return d + (((s - d) * a) >> 8)
+
+
+def _pixel_alpha_px(s, d, a):
+    if a == 0:
+        return d
+    if a == 255:
+        return s
+    return d + (((s - d) * a) >> 8)
+
+
+def blit_alpha(target, source, location, opacity):
+    """drawer.py:198-205.  target (H, W, 3) uint8 modified in place; source (h, w, 3 or 4) uint8."""
+    H, W, _ = target.shape
+    x0, y0 = int(location[0]), int(location[1])
+    h, w = source.shape[0], source.shape[1]
+    temp = np.zeros((h, w, 3), dtype=np.uint8)                   # Surface((w, h)).convert(): opaque black
+    for ty in range(h):                                          # temp.blit(target, (-x, -y))
+        for tx in range(w):
+            sx, sy = tx + x0, ty + y0
+            if 0 <= sx < W and 0 <= sy < H:
+                temp[ty, tx] = target[sy, sx]
+    for ty in range(h):                                          # temp.blit(source, (0, 0))
+        for tx in range(w):
+            px = source[ty, tx]
+            a = int(px[3]) if source.shape[2] == 4 else 255
+            temp[ty, tx] = [_pixel_alpha_px(int(px[c]), int(temp[ty, tx, c]), a) for c in range(3)]
+    opacity = int(opacity)                                       # temp.set_alpha(opacity); target.blit(temp, location)
+    for ty in range(h):
+        for tx in range(w):
+            sx, sy = tx + x0, ty + y0
+            if 0 <= sx < W and 0 <= sy < H:
+                target[sy, sx] = [_surface_alpha_px(int(temp[ty, tx, c]), int(target[sy, sx, c]), opacity) for c in range(3)]
+
+
+def _alphablit(dst, spr, ox, oy):
+    """pygame alphablit_alpha (ALPHA_BLEND) of an RGBA sprite onto an RGBA surface."""
+    H, W, _ = dst.shape
+    ox, oy = int(ox), int(oy)
+    for sy in range(spr.shape[0]):
+        y = oy + sy
+        if y < 0 or y >= H:
+            continue
+        for sx in range(spr.shape[1]):
+            x = ox + sx
+            if x < 0 or x >= W:
+                continue
+            sR, sG, sB, sA = (int(v) for v in spr[sy, sx])
+            dR, dG, dB, dA = (int(v) for v in dst[y, x])
+            if dA:
+                dR = ((dR << 8) + (sR - dR) * sA + sR) >> 8
+                dG = ((dG << 8) + (sG - dG) * sA + sG) >> 8
+                dB = ((dB << 8) + (sB - dB) * sA + sB) >> 8
+                dA = sA + dA - ((sA * dA) // 255)
+            else:
+                dR, dG, dB, dA = sR, sG, sB, sA
+            dst[y, x] = (dR, dG, dB, dA)
+
+
+class _Opaque:
+    """Adapter: the line / circle helpers above write 3-tuples; on a SRCALPHA surface the colour carries alpha 255."""
+
+    def __init__(self, rgba):
+        self.a = rgba
+        self.shape = rgba.shape
+
+    def __setitem__(self, idx, col):
+        self.a[idx] = (col[0], col[1], col[2], 255)
+
+
+def blend(level_text, snap, surf, alpha_objs, alpha_player):
+    """drawer.py:207-231: objects (but the handle bases) at opacity alpha_objs, the hero at alpha_player, blended
+    onto ``surf`` (H, W, 3) uint8 in place."""
+    H, W, _ = surf.shape
+    new_surf = np.zeros((H, W, 4), dtype=np.uint8)               # Surface(..., SRCALPHA, 32), :209
+    d = h = b = it = 0
+    for kind, cx, cy, _ in level_text.objects:                   # :211
+        if kind == K_HANDLE:                                     # :212-220
+            angle = ((math.pi / 2.0) * snap["angles"][h]) + math.pi / 4.0
+            h += 1
+            r = S * 0.75
+            start = (cx * S + S / 2, cy * S + S)
+            end = (int(start[0] + (r * math.cos(angle))), int(start[1] - (r * math.sin(angle))))
+            canvas = _Opaque(new_surf)
+            _line_width(canvas, (int(start[0]), int(start[1])), end, 5, (47, 79, 79))
+            _fill_circle(canvas, end[0], end[1], int(S / 10), (255, 0, 0))
+            _blit(surf, _scaled("handle_base"), cx * S, cy * S)  # straight onto surf, full opacity (:220)
+        elif kind == K_DOOR:                                     # draw_object(obj, new_surf), :222
+            _alphablit(new_surf, _scaled("door_closed" if snap["doors"][d] else "door_open"), cx * S, cy * S)
+            d += 1
+        elif kind in (K_KEY, K_GOLD):
+            x, y = snap["items"][it][0], snap["items"][it][1]
+            it += 1
+            if x < 0:
+                continue
+            _alphablit(new_surf, _scaled("key" if kind == K_KEY else "gold"), x, y)
+        elif kind == K_BOLT:
+            _alphablit(new_surf, _scaled("bolt_locked" if snap["bolts"][b] else "bolt_open"), cx * S, cy * S)
+            b += 1
+    blit_alpha(surf, new_surf, (0, 0), int(255 * alpha_objs))    # :223
+    hero = _scaled("hero")
+    if not snap["facing"]:
+        hero = hero[:, ::-1]
+    blit_alpha(surf, hero, (snap["px"] - S / 2, snap["py"]), int(255 * alpha_player))   # :225-231
+    return surf
