@@ -542,7 +542,7 @@ template <bool TAPE, int NI, int TILE>
 static cudaError_t step_tile(const BatchView &B, int tile, const int32_t *a, float *obs, float *rew, uint8_t *done,
                              uint8_t *ran, uint16_t *avail, cudaStream_t s) {
     const size_t smem = step_smem(B);
-    if (smem > 32 * 1024) {      // many layouts with long observations: opt in beyond the default 48 KB (static + dynamic)
+    {   // static + dynamic shared memory can pass the default 48 KB (large tiles, many layouts): opt in once per size
         static size_t allowed = 0;
         if (smem > allowed) {
             cudaError_t r = cudaFuncSetAttribute(tg_step_kernel<TAPE, NI, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
