@@ -12,7 +12,7 @@ SO = os.path.join(PKG, "libtreasure_b200.so")
 SOURCES = ["tg_step.cu", "tg_render.cu", "tg_blend.cu", "tg_capi.cu"]
 HEADERS = ["tg_types.h", "tg_device.cuh", "tg_launch.h", os.path.join("..", "..", "include", "treasure_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550"]
+              "-Xcompiler", "-fPIC,-fopenmp", "-shared", "-diag-suppress", "550", "-lgomp"]
 
 
 def nvcc_path():

@@ -60,6 +60,7 @@ _SIGNATURES = {
     "tg_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tg_step": (C.c_int, [C.c_void_p] * 8),
     "tg_step_host": (C.c_int, [C.c_void_p] * 7),
+    "tg_step_host_sparse": (C.c_int, [C.c_void_p] * 7),
     "tg_available_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tg_render": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "tg_blend": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
@@ -74,6 +75,7 @@ _SIGNATURES = {
     "tg_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tg_stats_clear": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tg_launch_count": (C.c_int64, [C.c_void_p]),
+    "tg_host_traffic": (None, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "tg_debug_phase_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 

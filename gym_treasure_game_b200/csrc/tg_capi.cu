@@ -3,7 +3,9 @@
 // tg_step.cu / tg_render.cu.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -63,9 +65,19 @@ struct tg_env {
     int32_t *s_actions = nullptr; float *s_obs = nullptr; float *s_reward = nullptr;
     uint8_t *s_done = nullptr; uint8_t *s_ran = nullptr;
     int64_t launches = 0;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;   // copied by the *_host entry points
     // tg_step_host pipeline: step kernel of chunk c+1 overlaps the device->host copies of chunk c
     cudaStream_t side = nullptr;
     cudaEvent_t ev_chunk[8] = {}, ev_join = nullptr;
+    // tg_step_host_sparse: device / pinned-host record buffers, per-chunk counters, and what the caller's host arrays
+    // are known to hold (they are only patched while `sp_primed` and the pointers have not changed)
+    uint32_t *sp_drecs = nullptr, *sp_dcount = nullptr;
+    uint32_t *sp_hrecs = nullptr, *sp_hcount = nullptr;      // cudaHostAlloc
+    cudaEvent_t ev_cnt[8] = {}, ev_rec[8] = {};
+    int sp_words = 0;
+    bool sp_primed = false, sp_dense_flags = false;
+    const void *sp_obs = nullptr, *sp_reward = nullptr, *sp_done = nullptr, *sp_ran = nullptr;
+    std::vector<uint32_t> sp_prev;                           // env indices patched by the previous sparse call
 };
 
 extern "C" const char *tg_last_error(void) { return g_err; }
@@ -252,6 +264,10 @@ static void free_env(tg_env *e) {
     if (e->side) cudaStreamDestroy(e->side);
     for (cudaEvent_t ev : e->ev_chunk) if (ev) cudaEventDestroy(ev);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
+    for (cudaEvent_t ev : e->ev_cnt) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->ev_rec) if (ev) cudaEventDestroy(ev);
+    if (e->sp_hrecs) cudaFreeHost(e->sp_hrecs);
+    if (e->sp_hcount) cudaFreeHost(e->sp_hcount);
     for (void *p : e->allocs) cudaFree(p);
     delete e;
 }
@@ -368,6 +384,10 @@ extern "C" void tg_destroy(tg_env *env) {
 extern "C" int64_t tg_num_envs(const tg_env *env) { return env ? env->B.n : 0; }
 extern "C" int32_t tg_obs_dim(const tg_env *env) { return env ? env->B.obs_dim : 0; }
 extern "C" int64_t tg_launch_count(const tg_env *env) { return env ? env->launches : 0; }
+extern "C" void tg_host_traffic(const tg_env *env, int64_t *h2d_bytes, int64_t *d2h_bytes) {
+    if (h2d_bytes) *h2d_bytes = env ? env->h2d_bytes : 0;
+    if (d2h_bytes) *d2h_bytes = env ? env->d2h_bytes : 0;
+}
 
 // ---------------------------------------------------------------------------
 // stream-ordered entry points
@@ -377,6 +397,7 @@ extern "C" int tg_reset(tg_env *env, const uint8_t *mask, float *obs, void *stre
     DeviceGuard guard(env->device);
     CU(launch_reset(env->B, env->ni, mask, obs, (cudaStream_t)stream));
     env->launches++;
+    env->sp_primed = false;
     return TG_OK;
 }
 
@@ -386,6 +407,7 @@ extern "C" int tg_step(tg_env *env, const int32_t *actions, float *obs, float *r
     DeviceGuard guard(env->device);
     CU(launch_step(env->B, env->ni, actions, obs, reward, done, ran, avail, (cudaStream_t)stream));
     env->launches++;
+    env->sp_primed = false;
     return TG_OK;
 }
 
@@ -419,6 +441,8 @@ extern "C" int tg_step_host(tg_env *env, const int32_t *actions, float *obs, flo
         CU(cudaEventCreateWithFlags(&env->ev_join, cudaEventDisableTiming));
     }
     CU(cudaMemcpyAsync(env->s_actions, actions, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    env->h2d_bytes += n * (int64_t)sizeof(int32_t);
+    env->d2h_bytes += n * ((obs ? (int64_t)od * 4 : 0) + (reward ? 4 : 0) + (done ? 1 : 0) + (ran ? 1 : 0));
     const int64_t per = ((n + chunks - 1) / chunks + 2047) / 2048 * 2048;      // tile-aligned chunk size
     for (int c = 0; c < chunks; c++) {
         const int64_t lo = (int64_t)c * per, cnt = (lo + per <= n) ? per : n - lo;
@@ -444,6 +468,126 @@ extern "C" int tg_step_host(tg_env *env, const int32_t *actions, float *obs, flo
         CU(cudaStreamWaitEvent(s, env->ev_join, 0));
     }
     CU(cudaStreamSynchronize(s));
+    // the caller's arrays now hold every env's outputs: tg_step_host_sparse may patch them from here on
+    env->sp_primed = obs && reward && done && ran;
+    env->sp_dense_flags = true;
+    env->sp_obs = obs; env->sp_reward = reward; env->sp_done = done; env->sp_ran = ran;
+    env->sp_prev.clear();
+    return TG_OK;
+}
+
+// Host side of the sparse step: patch the caller's arrays from `n` records (OpenMP: the rows are scattered over
+// tens of megabytes, one thread would spend longer here than the whole dense copy takes).
+static void sparse_apply(const uint32_t *recs, int64_t n, int words, int od, float *obs, float *reward, uint8_t *done,
+                         uint8_t *ran, uint32_t *touched) {
+#pragma omp parallel for schedule(static) if (n > 4096)
+    for (int64_t r = 0; r < n; r++) {
+        const uint32_t *rec = recs + r * words;
+        const uint32_t idx = rec[0];
+        touched[r] = idx;
+        memcpy(&reward[idx], &rec[1], 4);
+        done[idx] = (uint8_t)(rec[2] & 255u);
+        ran[idx] = (uint8_t)(rec[2] >> 8);
+        memcpy(obs + (size_t)idx * od, rec + 3, (size_t)od * 4);
+    }
+}
+
+extern "C" int tg_step_host_sparse(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done,
+                                   uint8_t *ran, void *stream) {
+    if (!env || !actions || !obs || !reward || !done || !ran) return fail(TG_ERR_ARG, "null argument");
+    if (!env->sp_primed || obs != env->sp_obs || reward != env->sp_reward || done != env->sp_done || ran != env->sp_ran)
+        return tg_step_host(env, actions, obs, reward, done, ran, stream);      // first call / other arrays: everything crosses
+    DeviceGuard guard(env->device);
+    int rc = ensure_staging(env);
+    if (rc != TG_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n = env->B.n;
+    const int od = env->B.obs_dim;
+    if (!env->sp_drecs) {
+        env->sp_words = (3 + od + 3) / 4 * 4;                                   // 16-byte records
+        CU(dev_alloc(env, &env->sp_drecs, (size_t)n * env->sp_words));
+        CU(dev_alloc(env, &env->sp_dcount, (size_t)8));
+        CU(cudaHostAlloc((void **)&env->sp_hrecs, (size_t)n * env->sp_words * 4, cudaHostAllocDefault));
+        CU(cudaHostAlloc((void **)&env->sp_hcount, 8 * sizeof(uint32_t), cudaHostAllocDefault));
+        for (int c = 0; c < 8; c++) {
+            CU(cudaEventCreateWithFlags(&env->ev_cnt[c], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&env->ev_rec[c], cudaEventDisableTiming));
+        }
+    }
+    if (!env->side) {
+        CU(cudaStreamCreateWithFlags(&env->side, cudaStreamNonBlocking));
+        for (int c = 0; c < 8; c++) CU(cudaEventCreateWithFlags(&env->ev_chunk[c], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&env->ev_join, cudaEventDisableTiming));
+    }
+    const int words = env->sp_words;
+    static const int dbg = getenv("TG_SPARSE_DEBUG") ? atoi(getenv("TG_SPARSE_DEBUG")) : 0;
+    static const int forced_chunks = getenv("TG_SPARSE_CHUNKS") ? atoi(getenv("TG_SPARSE_CHUNKS")) : 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
+    const auto t_0 = now();
+    int chunks = 1;
+    if (n >= (int64_t)4 * 131072) chunks = 2;        // the records are a fifth of the dense outputs: two chunks overlap enough
+    if (forced_chunks >= 1 && forced_chunks <= 8) chunks = forced_chunks;
+    const int64_t per = ((n + chunks - 1) / chunks + 2047) / 2048 * 2048;
+    CU(cudaMemcpyAsync(env->s_actions, actions, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    env->h2d_bytes += n * (int64_t)sizeof(int32_t);
+    CU(cudaMemsetAsync(env->sp_dcount, 0, 8 * sizeof(uint32_t), s));
+    int used = 0;
+    for (int c = 0; c < chunks; c++) {
+        const int64_t lo = (int64_t)c * per, cnt = (lo + per <= n) ? per : n - lo;
+        if (cnt <= 0) break;
+        BatchView V = env->B;
+        V.r_begin = lo; V.r_count = cnt;
+        V.sp_count = env->sp_dcount + c; V.sp_recs = env->sp_drecs + (size_t)lo * words; V.sp_words = words;
+        CU(launch_step(V, env->ni, env->s_actions, nullptr, nullptr, nullptr, nullptr, nullptr, s));
+        env->launches++;
+        CU(cudaEventRecord(env->ev_chunk[c], s));
+        CU(cudaStreamWaitEvent(env->side, env->ev_chunk[c], 0));
+        CU(cudaMemcpyAsync(env->sp_hcount + c, env->sp_dcount + c, sizeof(uint32_t), cudaMemcpyDeviceToHost, env->side));
+        CU(cudaEventRecord(env->ev_cnt[c], env->side));
+        used = c + 1;
+    }
+    // while the kernels run: clear what the previous call reported (or everything after a dense call)
+    if (env->sp_dense_flags) {
+        memset(reward, 0, (size_t)n * sizeof(float)); memset(done, 0, (size_t)n); memset(ran, 0, (size_t)n);
+        env->sp_dense_flags = false;
+    } else {
+        const int64_t np = (int64_t)env->sp_prev.size();
+        const uint32_t *prev = env->sp_prev.data();
+#pragma omp parallel for schedule(static) if (np > 4096)
+        for (int64_t k = 0; k < np; k++) { reward[prev[k]] = 0.0f; done[prev[k]] = 0; ran[prev[k]] = 0; }
+    }
+    env->sp_prev.clear();
+    const auto t_1 = now();
+    long t_cnt = 0, t_rec = 0, t_app = 0;
+    int64_t counts[8];
+    for (int c = 0; c < used; c++) {                 // record copies, sized by the counts as they arrive
+        const auto a0 = now();
+        CU(cudaEventSynchronize(env->ev_cnt[c]));
+        t_cnt += us(a0, now());
+        counts[c] = env->sp_hcount[c];
+        const size_t off = (size_t)c * per * words;
+        if (counts[c]) CU(cudaMemcpyAsync(env->sp_hrecs + off, env->sp_drecs + off, (size_t)counts[c] * words * 4, cudaMemcpyDeviceToHost, env->side));
+        CU(cudaEventRecord(env->ev_rec[c], env->side));
+    }
+    for (int c = 0; c < used; c++) {                 // patch chunk c while chunk c + 1 is still crossing
+        const auto a0 = now();
+        CU(cudaEventSynchronize(env->ev_rec[c]));
+        const auto a1 = now();
+        t_rec += us(a0, a1);
+        const uint32_t *recs = env->sp_hrecs + (size_t)c * per * words;
+        const size_t base = env->sp_prev.size();
+        env->sp_prev.resize(base + (size_t)counts[c]);
+        sparse_apply(recs, counts[c], words, od, obs, reward, done, ran, env->sp_prev.data() + base);
+        env->d2h_bytes += counts[c] * words * 4 + 4;
+        t_app += us(a1, now());
+    }
+    CU(cudaEventRecord(env->ev_join, env->side));
+    CU(cudaStreamWaitEvent(s, env->ev_join, 0));
+    CU(cudaStreamSynchronize(s));
+    if (dbg) fprintf(stderr, "[tg sparse] launch+clear %ld us, wait counts %ld, wait records %ld, patch %ld, total %ld us, %d chunks\n",
+                     us(t_0, t_1), t_cnt, t_rec, t_app, us(t_0, now()), used);
     return TG_OK;
 }
 
@@ -513,6 +657,7 @@ extern "C" int tg_set_state(tg_env *env, const tg_state_view *in, void *stream) 
     DeviceGuard guard(env->device);
     CU(launch_set_state(env->B, *in, (cudaStream_t)stream));
     env->launches++;
+    env->sp_primed = false;
     return TG_OK;
 }
 
@@ -521,6 +666,7 @@ extern "C" int tg_primitive_step(tg_env *env, const int32_t *actions, float *obs
     DeviceGuard guard(env->device);
     CU(launch_primitive(env->B, env->ni, actions, obs, reward, done, (cudaStream_t)stream));
     env->launches++;
+    env->sp_primed = false;
     return TG_OK;
 }
 
@@ -529,6 +675,7 @@ extern "C" int tg_init_with_state(tg_env *env, const double *states, const uint8
     DeviceGuard guard(env->device);
     CU(launch_init_with_state(env->B, env->ni, states, mask, (cudaStream_t)stream));
     env->launches++;
+    env->sp_primed = false;
     return TG_OK;
 }
 

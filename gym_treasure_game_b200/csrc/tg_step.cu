@@ -119,6 +119,7 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, const int32_t *__r
     __shared__ int sh_stats[8];
     __shared__ int hist[NBUCKET];
     __shared__ int next_chunk;
+    __shared__ uint32_t rec_base;
     __shared__ uint8_t ckey[TILE / 32], order[TILE / 32];   // length class of each runnable chunk; chunks longest first
     __shared__ uint32_t info[TILE];
     __shared__ uint16_t perm0[TILE];
@@ -206,6 +207,7 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, const int32_t *__r
     const int n_run = hist[NBUCKET - 1];                    // exclusive scan: start of bucket 63 (not runnable) = runnable envs
     const int nrc = (n_run + 31) >> 5;
     __syncthreads();
+    if (tid == STEP_THREADS - 1 && B.sp_count) rec_base = atomicAdd(B.sp_count, (uint32_t)n_run);    // sparse outputs: this tile's block of records
     if (tid < 32) {
         for (int c = lane; c < nrc; c += 32) ckey[c] = (uint8_t)(11 - ((info[perm[c * 32]] >> 8) & 63u) % 12u);
         __syncwarp();
@@ -289,6 +291,13 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, const int32_t *__r
                 }
             }
             B.acct[i] = acct;
+            if (B.sp_count) {                                                // sparse outputs: only an env that was reset (or stays done) reports
+                if (d) {
+                    uint32_t *rec = B.sp_recs + (size_t)atomicAdd(B.sp_count, 1u) * B.sp_words;
+                    rec[0] = (uint32_t)i; rec[1] = 0u; rec[2] = (uint32_t)d;
+                    write_obs(e, L, B.obs_lut + (size_t)lid * 2 * OBS_LUT_N, reinterpret_cast<float *>(rec + 3), od);
+                }
+            }
             if (obs) write_obs(e, L, B.obs_lut + (size_t)lid * 2 * OBS_LUT_N, stage + lane * od, od);
             if (reward) reward[i] = 0.0f;
             if (done_out) done_out[i] = (uint8_t)d;
@@ -342,6 +351,11 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, const int32_t *__r
             }
         }
         B.acct[i] = acct;
+        if (B.sp_count) {                                                    // sparse outputs: every env that ran reports
+            uint32_t *rec = B.sp_recs + (size_t)(rec_base + (uint32_t)j) * B.sp_words;
+            rec[0] = (uint32_t)i; rec[1] = __float_as_uint((float)r); rec[2] = (uint32_t)d | 256u;
+            write_obs(e, L, B.obs_lut + (size_t)lid * 2 * OBS_LUT_N, reinterpret_cast<float *>(rec + 3), od);
+        }
         if (obs) write_obs(e, L, B.obs_lut + (size_t)lid * 2 * OBS_LUT_N, obs + i * od, od);
         if (reward) reward[i] = (float)r;
         if (done_out) done_out[i] = (uint8_t)d;

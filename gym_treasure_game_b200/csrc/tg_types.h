@@ -93,6 +93,12 @@ struct BatchView {
     const int64_t *tape_off;
     unsigned long long *stats;   // [8]
     const float *obs_lut;        // [n_levels][2][OBS_LUT_N]
+    // sparse outputs (tg_step_host_sparse), or sp_count == NULL: one record of sp_words 32-bit words per env whose
+    // outputs are not (obs unchanged, reward 0, done 0, ran 0): [0] env index, [1] reward (float bits),
+    // [2] done | ran << 8, [3 ..] observation
+    uint32_t *sp_count;
+    uint32_t *sp_recs;
+    int32_t sp_words;
     unsigned long long *phase_ts; // debug: [grid][8] globaltimer stamps of the step kernel's phases, or NULL
 };
 

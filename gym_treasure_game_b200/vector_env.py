@@ -191,6 +191,14 @@ class VectorTreasureGame:
                                    _ptr(host["done"]), _ptr(host["ran"]), self._stream()))
         return host
 
+    def step_host_sparse(self, host: Optional[Dict[str, torch.Tensor]] = None):
+        """``step_host`` with only the changed envs crossing the bus (``tg_step_host_sparse``): the host arrays must
+        be the ones the previous ``step_host`` / ``step_host_sparse`` call filled; the result is the same."""
+        host = host or self._host or self.make_host_buffers()
+        check(self._L.tg_step_host_sparse(self._h, _ptr(host["actions"]), _ptr(host["obs"]), _ptr(host["reward"]),
+                                          _ptr(host["done"]), _ptr(host["ran"]), self._stream()))
+        return host
+
     @property
     def available_mask(self) -> torch.Tensor:
         """``TreasureGame.available_mask`` (treasure_game.py:83-89): (N, 9) uint8."""
@@ -337,6 +345,12 @@ class VectorTreasureGame:
 
     def clear_stats(self) -> None:
         check(self._L.tg_stats_clear(self._h, self._stream()))
+
+    def host_traffic(self):
+        """(host->device, device->host) bytes copied so far by ``step_host`` / ``step_host_sparse``."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._L.tg_host_traffic(self._h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
 
     @property
     def launch_count(self) -> int:

@@ -151,6 +151,15 @@ int tg_step(tg_env *env, const int32_t *actions, float *obs, float *reward, uint
 int tg_step_host(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done,
                  uint8_t *ran, void *stream);
 
+/* Same results in the same HOST arrays, but only what changed crosses the bus: an option that cannot run leaves its
+ * env untouched (_option.py:22-23), so under the previous call's arrays only the envs that ran or were reset need
+ * new rows.  The kernel compacts those into records on the device; the call copies the records and patches the
+ * arrays (host threads).  Contract: obs / reward / done / ran are the arrays the previous tg_step_host or
+ * tg_step_host_sparse call of this env filled, unmodified in `obs`; otherwise (first call, other pointers, or any
+ * other state-changing call in between) the call falls back to tg_step_host.  All four outputs are required. */
+int tg_step_host_sparse(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done,
+                        uint8_t *ran, void *stream);
+
 /* TreasureGame.available_mask (treasure_game.py:83-89).  mask DEV [N][9] u8. */
 int tg_available_mask(tg_env *env, uint8_t *mask, void *stream);
 
@@ -211,6 +220,8 @@ int tg_debug_phase_buffer(tg_env *env, uint64_t *stamps);
 
 /* how many kernels this library has launched on behalf of `env` (bench bookkeeping) */
 int64_t tg_launch_count(const tg_env *env);
+/* bytes the tg_step_host* calls of `env` have copied host->device / device->host so far (bench bookkeeping) */
+void tg_host_traffic(const tg_env *env, int64_t *h2d_bytes, int64_t *d2h_bytes);
 
 #ifdef __cplusplus
 }

@@ -54,3 +54,29 @@ def test_seed_reproducibility():
         outs.append(tr)
         e.close()
     assert outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("n", [1000, 300000])
+def test_step_host_sparse_equals_dense(n):
+    """tg_step_host_sparse patches the host arrays of the previous call; after every step they must equal what the
+    dense tg_step_host of a twin batch delivers (obs, reward, done, ran), including resets and the fallbacks."""
+    import torch
+    from gym_treasure_game_b200 import VectorTreasureGame
+    a = VectorTreasureGame(n, seed=5, max_episode_steps=7, auto_reset=True, render=False)
+    b = VectorTreasureGame(n, seed=5, max_episode_steps=7, auto_reset=True, render=False)
+    ha, hb = a.make_host_buffers(), b.make_host_buffers()
+    g = torch.Generator().manual_seed(3)
+    d2h0 = a.host_traffic()[1]
+    for t in range(24):
+        acts = torch.randint(0, 9, (n,), generator=g, dtype=torch.int32)
+        ha["actions"].copy_(acts); hb["actions"].copy_(acts)
+        if t == 12:
+            a.reset(); b.reset()                      # a device-side call in between: the next sparse call must fall back
+        a.step_host_sparse(ha)
+        b.step_host(hb)
+        for k in ("obs", "reward", "done", "ran"):
+            assert torch.equal(ha[k], hb[k]), (t, k)
+    sparse_bytes = a.host_traffic()[1] - d2h0
+    dense_bytes = b.host_traffic()[1]
+    assert sparse_bytes < 0.6 * dense_bytes           # 2 dense fallbacks + 22 sparse steps
+    assert a.stats() == b.stats()
