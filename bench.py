@@ -321,7 +321,8 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": 1000.0 * total_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1000.0 * total_s / K, "ms_per_step_median": sorted(per_step_ms)[K // 2], "ms_per_step_max": max(per_step_ms),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32+f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs_per_gpu": n, "total_envs": n * world, "max_episode_steps": MAX_EPISODE_STEPS,
                    "l2": "512 MiB buffer overwritten between timed steps (outside the event pairs)",

@@ -11,6 +11,8 @@
 #include <new>
 #include <vector>
 
+#include <omp.h>
+
 #include "tg_launch.h"
 
 using namespace tg;
@@ -476,11 +478,31 @@ extern "C" int tg_step_host(tg_env *env, const int32_t *actions, float *obs, flo
     return TG_OK;
 }
 
+// Threads for the host-side patching: the host cores divided among the visible devices (one process per GPU), 2..16;
+// TG_HOST_THREADS overrides.  Passed as a num_threads clause because launchers such as torchrun export
+// OMP_NUM_THREADS=1, which would leave one thread to scatter 200 k rows.
+static int host_threads() {
+    static int t = 0;
+    if (!t) {
+        const char *v = getenv("TG_HOST_THREADS");
+        int want = v ? atoi(v) : 0;
+        if (want < 1) {
+            int ndev = 0;
+            if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); ndev = 1; }
+            want = omp_get_num_procs() / ndev;
+            if (want > 16) want = 16;
+            if (want < 2) want = 2;
+        }
+        t = want > 64 ? 64 : want;
+    }
+    return t;
+}
+
 // Host side of the sparse step: patch the caller's arrays from `n` records (OpenMP: the rows are scattered over
 // tens of megabytes, one thread would spend longer here than the whole dense copy takes).
 static void sparse_apply(const uint32_t *recs, int64_t n, int words, int od, float *obs, float *reward, uint8_t *done,
                          uint8_t *ran, uint32_t *touched) {
-#pragma omp parallel for schedule(static) if (n > 4096)
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (n > 4096)
     for (int64_t r = 0; r < n; r++) {
         const uint32_t *rec = recs + r * words;
         const uint32_t idx = rec[0];
@@ -555,7 +577,7 @@ extern "C" int tg_step_host_sparse(tg_env *env, const int32_t *actions, float *o
     } else {
         const int64_t np = (int64_t)env->sp_prev.size();
         const uint32_t *prev = env->sp_prev.data();
-#pragma omp parallel for schedule(static) if (np > 4096)
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (np > 4096)
         for (int64_t k = 0; k < np; k++) { reward[prev[k]] = 0.0f; done[prev[k]] = 0; ran[prev[k]] = 0; }
     }
     env->sp_prev.clear();
