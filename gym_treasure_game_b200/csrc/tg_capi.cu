@@ -481,7 +481,7 @@ extern "C" int tg_step_host(tg_env *env, const int32_t *actions, float *obs, flo
 // Threads for the host-side patching: the host cores divided among the visible devices (one process per GPU), 2..16;
 // TG_HOST_THREADS overrides.  Passed as a num_threads clause because launchers such as torchrun export
 // OMP_NUM_THREADS=1, which would leave one thread to scatter 200 k rows.
-static int host_threads() {
+__attribute__((used)) static int host_threads() {   // referenced from OpenMP clauses only (the CUDA front end does not see those)
     static int t = 0;
     if (!t) {
         const char *v = getenv("TG_HOST_THREADS");

@@ -80,3 +80,30 @@ def test_step_host_sparse_equals_dense(n):
     dense_bytes = b.host_traffic()[1]
     assert sparse_bytes < 0.6 * dense_bytes           # 2 dense fallbacks + 22 sparse steps
     assert a.stats() == b.stats()
+
+
+def test_step_host_sparse_mixed_layouts():
+    """Sparse records with several layouts in one batch: observation rows of different lengths (zero padded),
+    the generic observation program and the 4-item kernels."""
+    import os, sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import gen_golden
+    from gpu_util import product_level
+    from gym_treasure_game_b200 import VectorTreasureGame
+    lv = gen_golden.variant_levels()
+    names = ["default", "mirror", "twin", "altinit"]
+    n = 4099                                                    # ragged: the last tile is not a multiple of 32
+    ids = np.random.default_rng(2).integers(0, len(names), n).astype(np.uint8)
+    mk = lambda: VectorTreasureGame(n, seed=8, max_episode_steps=9, auto_reset=True, render=False,
+                                    levels=[product_level(lv[k]) for k in names], level_ids=ids)
+    a, b = mk(), mk()
+    ha, hb = a.make_host_buffers(), b.make_host_buffers()
+    g = torch.Generator().manual_seed(6)
+    for t in range(30):
+        acts = torch.randint(0, 9, (n,), generator=g, dtype=torch.int32)
+        ha["actions"].copy_(acts); hb["actions"].copy_(acts)
+        a.step_host_sparse(ha); b.step_host(hb)
+        for k in ("obs", "reward", "done", "ran"):
+            assert torch.equal(ha[k], hb[k]), (t, k)
+    assert a.obs_dim > 9 and a.stats() == b.stats()
