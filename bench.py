@@ -40,7 +40,7 @@ WORKLOAD = ("treasure_game-v0 vector-state obs, 1,048,576 envs per GPU (BASELINE
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.01):
+    def __init__(self, index, period=0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
