@@ -29,10 +29,10 @@ struct Env {
     uint32_t d0, w0, w1, w2, w3;    // draw index at the start of this API call, cached Philox block
     uint32_t key0, key1, id_lo, id_hi;
     const double *tape;             // parity mode: this env's slice of the draw tape
-    // row-mask cache for the two probes every tick makes (valid while playery == m_py and the doors
+    // row-mask cache for the probes every tick makes (valid while the probed pair of rows is the one in the key and the doors
     // do not move): m_fall = non-open cells of the rows of y and y+50, m_side = solid cells of the
     // rows of y+4 and y+44; bit = padded column.  A walk never changes y, so its ticks only shift/test.
-    int m_py, m_py_side;         // playery each mask was built for (INT_MIN = empty)
+    int m_py, m_py_side;         // key of the row pair each mask was built for: r_a | r_b << 8 | kind << 16 (INT_MIN = empty)
     uint32_t m_fall, m_side;
     // where this env's handle angles live (touched only by interact / reset / obs)
     double *angles;              // angles[h * n] is handle h
@@ -177,30 +177,46 @@ __device__ __forceinline__ uint32_t door_bits(const LevelBlob &L, uint32_t flags
     const uint32_t closed = (flags >> F_DOORS) & 63u;
     return li ? L.door_lut[li - 1][closed] : 0u;
 }
+// A mask depends on playery only through the two padded rows its probes fall in, so the cache is keyed by the row
+// pair: a fall moves one pixel at a time and re-probes after every pixel (impl:341-346) -- 47 of 48 are hits.
+// The fall slot also serves up_clear (impl:232-238; same cells kind, other rows: kind bit in the key) -- a jump's
+// rise evaluates up_clear every tick and never can_fall, its descent the other way round.
+__device__ __forceinline__ int fall_key(int py) { return pad_cell(py) | (pad_cell(py + 50) << 8); }
+__device__ __forceinline__ int upc_key(int py) { return pad_cell(py - 4) | (pad_cell(py - 1) << 8) | (1 << 16); }
+__device__ __forceinline__ int side_key(int py) { return pad_cell(py + 4) | (pad_cell(py + 44) << 8); }
 template <int NI>
-__device__ __forceinline__ void fall_cache_fill(Env<NI> &e, const LevelBlob &L) {
-    const int r0 = pad_cell(e.py), r1 = pad_cell(e.py + 50);
+__device__ __forceinline__ void fall_cache_fill(Env<NI> &e, const LevelBlob &L, int key) {
+    const int r0 = key & 255, r1 = (key >> 8) & 255;
     e.m_fall = L.row_nonopen[r0] | door_bits(L, e.flags, r0) | L.row_nonopen[r1] | door_bits(L, e.flags, r1);
-    e.m_py = e.py;
+    e.m_py = key;
 }
 template <int NI>
-__device__ __forceinline__ void side_cache_fill(Env<NI> &e, const LevelBlob &L) {
-    const int r2 = pad_cell(e.py + 4), r3 = pad_cell(e.py + 44);
+__device__ __forceinline__ void side_cache_fill(Env<NI> &e, const LevelBlob &L, int key) {
+    const int r2 = key & 255, r3 = (key >> 8) & 255;
     e.m_side = L.row_solid[r2] | door_bits(L, e.flags, r2) | L.row_solid[r3] | door_bits(L, e.flags, r3);
-    e.m_py_side = e.py;
+    e.m_py_side = key;
 }
 template <int NI>
 __device__ __forceinline__ void row_cache_drop(Env<NI> &e) { e.m_py = INT_MIN; e.m_py_side = INT_MIN; }
 // impl:283-288 through the cache
 template <int NI>
 __device__ __forceinline__ bool can_fall_m(Env<NI> &e, const LevelBlob &L) {
-    if (e.m_py != e.py) fall_cache_fill(e, L);
+    const int key = fall_key(e.py);
+    if (e.m_py != key) fall_cache_fill(e, L, key);
     return (((e.m_fall >> pad_cell(e.px - 10)) | (e.m_fall >> pad_cell(e.px + 10))) & 1u) == 0u;
+}
+// impl:232-238 through the cache: (x + {-4,0,4}, y + {-4..-1}) all OPEN; the probes span <= 2 columns and <= 2 rows
+template <int NI>
+__device__ __forceinline__ bool up_clear_m(Env<NI> &e, const LevelBlob &L) {
+    const int key = upc_key(e.py);
+    if (e.m_py != key) fall_cache_fill(e, L, key);
+    return (((e.m_fall >> pad_cell(e.px - 4)) | (e.m_fall >> pad_cell(e.px + 4))) & 1u) == 0u;
 }
 // impl:259-281 through the cache (x = playerx -+ 16)
 template <int NI>
 __device__ __forceinline__ bool side_free_m(Env<NI> &e, const LevelBlob &L, int x) {
-    if (e.m_py_side != e.py) side_cache_fill(e, L);
+    const int key = side_key(e.py);
+    if (e.m_py_side != key) side_cache_fill(e, L, key);
     return ((e.m_side >> pad_cell(x)) & 1u) == 0u;
 }
 // impl:240-257 in mask form: up: y > 1 and LADDER in rows of y-4, y, y+44; down: rows of y, next, y+51; columns of x-+12
@@ -379,7 +395,7 @@ __device__ __forceinline__ void tick(Env<NI> &e, const LevelBlob &L, int act, in
             else yd = d;
         }
     } else if (act == A_JUMP) {
-        if (!ladder_probe(L, e.px, e.py, false) && up_clear(L, e.flags, e.px, e.py))
+        if (!ladder_probe(L, e.px, e.py, false) && up_clear_m(e, L))
             e.flags = set_ticker(e.flags, draw_k<TAPE>(e) > (1ull << 51) ? 23 : 22);   // impl:316-319: random() > 0.25
     } else if (act == A_INTERACT) {
         interact<TAPE>(e, L);
@@ -387,7 +403,7 @@ __device__ __forceinline__ void tick(Env<NI> &e, const LevelBlob &L, int act, in
     }
     int tk = ticker(e.flags);
     if (tk > 0) {                                                                    // impl:331-334
-        if (up_clear(L, e.flags, e.px, e.py)) yd = -4;
+        if (up_clear_m(e, L)) yd = -4;
         e.flags = set_ticker(e.flags, tk - 1);
     } else if (can_fall_m(e, L)) {                                                   // impl:335-337
         yd = 4;
@@ -563,8 +579,8 @@ __device__ __forceinline__ int run_option_to_end(Env<NI> &e, const LevelBlob &L,
         // by noisy() if the side probe is free (and face that way), pick up.  playery never changes, so the
         // two row masks are loop constants.  Any other situation (ticker > 0, can_fall) leaves the loop
         // *before* the tick is executed and the general loop below takes over from the same state.
-        if (e.m_py != e.py) fall_cache_fill(e, L);
-        if (e.m_py_side != e.py) side_cache_fill(e, L);
+        if (e.m_py != fall_key(e.py)) fall_cache_fill(e, L, fall_key(e.py));
+        if (e.m_py_side != side_key(e.py)) side_cache_fill(e, L, side_key(e.py));
         const uint32_t mside = e.m_side, mfall = e.m_fall;
         // Inside [px .. bound] (walk_safe_bound) a tick is just "count, move by noisy()": no probe can change,
         // the target is not reached, nothing can be picked up.  Such ticks run without any check as long as the
