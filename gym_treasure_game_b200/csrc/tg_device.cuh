@@ -410,7 +410,12 @@ __device__ __forceinline__ void tick(Env<NI> &e, const LevelBlob &L, int act, in
     }
     e.px += xd;                                                                      // impl:339
     if (yd > 0 && can_fall_m(e, L)) {                                                // impl:341-346
-        do {
+        // The reference moves one pixel at a time and re-probes can_fall after each.  The probe only depends on the
+        // rows of y and y + 50: while y mod 48 stays below 46 they do not change, so every re-probe repeats the one
+        // above and the whole move goes through.
+        const int q = e.py + PAD * S - S * pad_cell(e.py);                           // y mod 48 (pad_cell = floor(y / 48) + PAD)
+        if (q + yd <= 45) e.py += yd;
+        else do {
             e.py++; yd--;
             if (!can_fall_m(e, L)) yd = 0;
         } while (yd > 0);
