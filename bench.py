@@ -407,6 +407,22 @@ def aux_configs(torch, dev, peak):
                              "roofline_frac": n * ALGO_BYTES_PER_ENV_STEP / t / 1e9 / peak}
     env.close()
 
+    # configs[2] read as strong scaling: 1,048,576 envs over 8 GPUs = 131,072 envs per GPU (the main line above is the
+    # weak-scaling reading, 1,048,576 envs per GPU)
+    n = 131072
+    env = VectorTreasureGame(n, device=dev, seed=0, max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True, render=False)
+    pool = [torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device=dev) for _ in range(64)]
+
+    def step131k():
+        env.step_raw(pool[it[0] % 64]); it[0] += 1
+    for _ in range(100):
+        step131k()
+    t = timed(step131k, 200)
+    out["cfg3_strong_shard_131072_envs"] = {"env_steps_per_s": n / t, "ms_per_step": t * 1e3,
+                                            "roofline_frac": n * ALGO_BYTES_PER_ENV_STEP / t / 1e9 / peak,
+                                            "note": "one GPU's shard when 1,048,576 envs are split over 8 GPUs"}
+    env.close()
+
     # configs[3]: 16384 envs, RGB observations
     n = 16384
     env = VectorTreasureGame(n, device=dev, seed=0, max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True, render=True)
