@@ -98,9 +98,11 @@ __device__ __forceinline__ void scan64(int *hist, int lane) {
 //            (measured: can_run + length estimate were 30 % of the kernel's warp instructions at 2-6 active lanes)
 //   phase 1  in option order: evaluate can_run of the chosen option (+ target column), estimate its
 //            length in ticks; histogram the (code path, length) classes
-//   phase 2  counting sort of the tile by class -> perm[]                (shared-memory atomics)
-//   phase 3  warps pull 32-env chunks of perm[] from a shared counter; a lane runs its env's option
-//            to termination, then reward / done / time-limit / auto-reset / obs / stores.
+//   phase 2  counting sort of the runnable envs by class -> perm[]; their 32-env chunks ordered longest first
+//   phase 3  warps pull chunks from a shared counter: first the runnable chunks (a lane runs its env's option to
+//            termination and puts the state back), then every index-order chunk for the envs whose option did not
+//            run: time-limit / auto-reset / outputs with contiguous loads and full-line stores
+//   phase 5  (after a barrier) the envs that ran: reward / done / time-limit / auto-reset / outputs
 // Sorting puts the ~10-20 % runnable envs of a tile into a few full warps of similar length
 // instead of leaving 1-2 busy lanes in every warp (measured SIMT efficiency before: 2/32 lanes).
 // Results do not depend on the order: every env owns its RNG stream and state.
