@@ -228,7 +228,7 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, const int32_t *__r
     const int od = B.obs_dim;
     float *stage = reinterpret_cast<float *>(smem_raw + (((size_t)B.n_levels * sizeof(LevelBlob) + 15) & ~(size_t)15))
                    + (size_t)(tid >> 5) * 32 * od;                             // this warp's [32][obs_dim] rows
-    const bool vec_ok = obs && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0);
+    const bool vec_ok = obs && ((reinterpret_cast<uintptr_t>(obs + base * od) & 15u) == 0);    // this tile's rows start on 16 bytes
 
     // ---- phase 3: one queue of 32-env chunks from a shared counter.  First the runnable envs (class-sorted chunks,
     // longest first): a lane runs its env's option to termination and puts the state back; info[el] becomes bits
@@ -587,7 +587,7 @@ static cudaError_t step_impl(const BatchView &B, int tile, const int32_t *a, flo
 int pick_step_tile(int64_t n) {
     static int forced = -1, slots = 0;
     if (forced < 0) { const char *v = getenv("TG_STEP_TILE"); forced = v ? atoi(v) : 0; }
-    if (forced >= 32 && forced <= 4096) return forced;
+    if (forced >= 32 && forced <= 4096) return (forced + 3) / 4 * 4;
     if (!slots) {
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
