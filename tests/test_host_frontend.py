@@ -74,3 +74,34 @@ def test_shard_range_partitions():
         assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
         sizes = [hi - lo for lo, hi in ranges]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_image_writers_roundtrip(tmp_path):
+    """draw_to_file's writers (PNG through zlib, 24-bit BMP) decode back to the same pixels (no GPU, no PIL)."""
+    import struct
+    import zlib
+    import numpy as np
+    from gym_treasure_game_b200.imageio import save_rgb
+    img = np.random.default_rng(3).integers(0, 256, (13, 7, 3), dtype=np.uint8)     # odd width: BMP row padding
+    png, bmp = str(tmp_path / "a.png"), str(tmp_path / "a.bmp")
+    save_rgb(png, img); save_rgb(bmp, img)
+    data = open(png, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, chunks = 8, {}
+    while pos < len(data):
+        n, tag = struct.unpack(">I4s", data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + body) & 0xFFFFFFFF
+        chunks[tag] = body
+        pos += 12 + n
+    assert struct.unpack(">IIBBBBB", chunks[b"IHDR"]) == (7, 13, 8, 2, 0, 0, 0)
+    rows = np.frombuffer(zlib.decompress(chunks[b"IDAT"]), dtype=np.uint8).reshape(13, 1 + 21)
+    assert not rows[:, 0].any() and np.array_equal(rows[:, 1:].reshape(13, 7, 3), img)
+    raw = open(bmp, "rb").read()
+    off, w, h, bpp = struct.unpack("<I", raw[10:14])[0], *struct.unpack("<ii", raw[18:26]), struct.unpack("<H", raw[28:30])[0]
+    assert (w, h, bpp) == (7, 13, 24)
+    stride = (3 * w + 3) // 4 * 4
+    body = np.frombuffer(raw[off:], dtype=np.uint8).reshape(h, stride)[:, :3 * w].reshape(h, w, 3)
+    assert np.array_equal(body[::-1, :, ::-1], img)
+    with pytest.raises(ValueError):
+        save_rgb(png, img[:, :, 0])
