@@ -125,7 +125,7 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, const int32_t *__r
     __shared__ uint8_t ckey[TILE / 32], order[TILE / 32];   // length class of each runnable chunk; chunks longest first
     __shared__ uint32_t info[TILE];
     __shared__ uint16_t perm0[TILE];
-    __shared__ uint16_t perm[TILE];
+    uint16_t *const perm = perm0;                            // the class order replaces the option order (dead after phase 1)
     const int tid = threadIdx.x, lane = tid & 31;
     phase_stamp(B, 0);
     if (tid < 8) sh_stats[tid] = 0;
