@@ -146,3 +146,30 @@ def test_drawer_object_and_draw_to_file(tmp_path):
     env.drawer.blend(surf, 0.5, 0.5)
     assert not torch.equal(surf, env.drawer.draw_background_to_surface())
     env.close()
+
+
+def test_blend_and_frames_on_random_layouts():
+    """Messy generated layouts (objects next to ladders and doors, several handles / bolts / keys): one rendered frame
+    and one accumulated blend per layout against the CPU restatement."""
+    from level_fuzz import random_level
+    from test_fuzz_levels import SEEDS
+    from gym_treasure_game_b200 import VectorTreasureGame
+    for seed in SEEDS[3:6]:
+        lvt = random_level(seed)
+        n = 8
+        env = VectorTreasureGame(n, seed=seed, auto_reset=False, levels=[product_level(lvt)])
+        cb = c_oracle.CBatch(c_oracle.CLevel(lvt), n, first_env_id=0, seed=seed)
+        cb.reset()
+        _advance(env, cb, 25, seed)
+        bg = ro.background(lvt.tiles)
+        frame = env.render(first=5, count=1)[0].cpu().numpy()
+        want = ro.render_frame(lvt, cb.snapshot(5), bg)
+        assert np.array_equal(frame, want), (seed, int((frame != want).sum()))
+        surf = torch.from_numpy(bg.copy()).cuda().contiguous()
+        env.blend(surf, 0.45, 0.8, first=2, count=3, accumulate=True)
+        want = bg.copy()
+        for i in range(2, 5):
+            ro.blend(lvt, cb.snapshot(i), want, 0.45, 0.8)
+        got = surf.cpu().numpy()
+        assert np.array_equal(got, want), (seed, int((got != want).sum()))
+        env.close()
