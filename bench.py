@@ -335,7 +335,7 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": (n * ALGO_BYTES_PER_ENV_STEP) / (total_s / K) / 1e9,
                      "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
-                     "kernel": "tg_step_kernel<false,2,2048>", "algorithmic_bytes_per_launch": n * ALGO_BYTES_PER_ENV_STEP,
+                     "kernel": "tg_step_kernel<false,2,4096> (2364-env tiles, 444 CTAs)", "algorithmic_bytes_per_launch": n * ALGO_BYTES_PER_ENV_STEP,
                      "note": "instruction-issue / serial-chain bound, not HBM bound (DESIGN.md 3.1); see work.primitive_ticks_per_s"},
         "work": {"runnable_fraction": stats["runnable_steps"] / max(stats["gym_steps"], 1),
                  "primitive_ticks_per_step": stats["primitive_ticks"] / max(stats["gym_steps"], 1),

@@ -108,7 +108,8 @@ __device__ __forceinline__ void scan64(int *hist, int lane) {
 // Results do not depend on the order: every env owns its RNG stream and state.
 // ---------------------------------------------------------------------------
 #ifndef TG_STEP_MIN_BLOCKS
-#define TG_STEP_MIN_BLOCKS 4      // 64 registers: 4 CTAs per SM (measured 4.81 vs 4.26 G env-steps/s at 74 registers)
+#define TG_STEP_MIN_BLOCKS 3      // 80 registers, no spills, 3 CTAs per SM with 2364-env tiles: 9.9 G env-steps/s; 64 registers x 4 CTAs with
+                                  // 1772-env tiles spilled 132 bytes: 9.2 G (round 1, v10 kernel; the v4 kernel had preferred 64 registers)
 #endif
 template <bool TAPE, int NI, int TILE>
 __global__ void __launch_bounds__(STEP_THREADS, TG_STEP_MIN_BLOCKS)
@@ -581,9 +582,9 @@ static cudaError_t step_impl(const BatchView &B, int tile, const int32_t *a, flo
 }
 
 // Tile size: large tiles sort better (more runnable envs per tile -> fuller warps); small tiles give more
-// CTAs.  The grid is sized in whole "slots": 148 SMs x 4 resident CTAs = 592 CTAs run at once, so the tile is
-// n / (592 * waves) rounded up -- with 2048-env tiles a 1,048,576-env step had 512 CTAs, 68 SMs held four of
-// them and 80 SMs three.  Smaller batches aim for two, then one CTA per SM slot.  TG_STEP_TILE overrides.
+// CTAs.  The grid is sized in whole "slots": 148 SMs x 3 resident CTAs = 444 CTAs run at once, so the tile is
+// n / (444 * waves) rounded up (2364 envs for a 1,048,576-env step) -- with fixed 2048-env tiles and 4 CTAs per SM a
+// step had 512 CTAs, 68 SMs held four of them and 80 SMs three.  Smaller batches aim for two, then one CTA per SM slot.  TG_STEP_TILE overrides.
 int pick_step_tile(int64_t n) {
     static int forced = -1, slots = 0;
     if (forced < 0) { const char *v = getenv("TG_STEP_TILE"); forced = v ? atoi(v) : 0; }
@@ -593,7 +594,7 @@ int pick_step_tile(int64_t n) {
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         slots = sms * TG_STEP_MIN_BLOCKS;
     }
-    const int64_t cap = 2048;
+    const int64_t cap = 4096;
     int64_t ctas;
     if (n >= (int64_t)slots * 512) ctas = (n + slots * cap - 1) / (slots * cap) * slots;      // whole waves of full occupancy
     else if (n >= (int64_t)slots * 128) ctas = slots / 2;                                      // two CTAs per SM
