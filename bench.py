@@ -317,7 +317,16 @@ def main():
         return world * n * Ke / float(dt.item()), (h1 - h0) // Ke, (d1 - d0) // Ke
 
     dense_value, dense_h2d, dense_d2h = time_host(env.step_host)
-    e2e_value, h2d, d2h = time_host(env.step_host_sparse)
+    sparse_value, sparse_h2d, sparse_d2h = time_host(env.step_host_sparse)
+    # both are public entry points with the same results; the line's e2e is the faster one on this box (the sparse
+    # path trades bus bytes for host-side patching, which several ranks sharing one host can lose), the other is kept
+    paths = {"tg_step_host_sparse": {"value": sparse_value, "h2d_bytes_per_step": sparse_h2d, "d2h_bytes_per_step": sparse_d2h,
+                                     "api": "tg_step_host_sparse (pinned host buffers; H2D actions, chunked step kernels that compact the envs whose outputs changed into records, D2H of the records, host threads patch obs/reward/done/ran in place; stream sync inside the call; bytes counted by the library per copy)"},
+             "tg_step_host": {"value": dense_value, "h2d_bytes_per_step": dense_h2d, "d2h_bytes_per_step": dense_d2h,
+                              "api": "tg_step_host (pinned host buffers; H2D actions, chunked step kernels overlapping the D2H of every env's obs/reward/done/ran; stream sync inside the call; bytes counted by the library per copy)"}}
+    best = max(paths, key=lambda k: paths[k]["value"])
+    other = [k for k in paths if k != best][0]
+    e2e_value, h2d, d2h = paths[best]["value"], paths[best]["h2d_bytes_per_step"], paths[best]["d2h_bytes_per_step"]
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -329,9 +338,7 @@ def main():
                    "actions": "torch.randint on the device before every step, outside the timed event pair", "collective": "NCCL all-reduce of int64[8] stats every 100 steps, side stream"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                "api": "tg_step_host_sparse (pinned host buffers; H2D actions, chunked step kernels that compact the envs whose outputs changed into records, D2H of the records, host threads patch obs/reward/done/ran in place; stream sync inside the call; bytes counted by the library per copy)",
-                "dense": {"value": dense_value, "h2d_bytes_per_step": dense_h2d, "d2h_bytes_per_step": dense_d2h,
-                          "api": "tg_step_host (every env's obs/reward/done/ran crosses the bus)"}},
+                "api": paths[best]["api"], "other_path": dict(paths[other], name=other)},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": (n * ALGO_BYTES_PER_ENV_STEP) / (total_s / K) / 1e9,
                      "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
