@@ -575,9 +575,7 @@ template <bool TAPE, int NI>
 static cudaError_t step_impl(const BatchView &B, int tile, const int32_t *a, float *obs, float *rew, uint8_t *done,
                              uint8_t *ran, uint16_t *avail, cudaStream_t s) {
     if (tile <= 256) return step_tile<TAPE, NI, 256>(B, tile, a, obs, rew, done, ran, avail, s);     // capacity of the shared arrays
-    if (tile <= 512) return step_tile<TAPE, NI, 512>(B, tile, a, obs, rew, done, ran, avail, s);
     if (tile <= 1024) return step_tile<TAPE, NI, 1024>(B, tile, a, obs, rew, done, ran, avail, s);
-    if (tile <= 2048) return step_tile<TAPE, NI, 2048>(B, tile, a, obs, rew, done, ran, avail, s);
     return step_tile<TAPE, NI, 4096>(B, tile, a, obs, rew, done, ran, avail, s);
 }
 
