@@ -622,6 +622,40 @@ __device__ __forceinline__ int run_option_to_end(Env<NI> &e, const LevelBlob &L,
         }
         e.total_actions += n;
         if (done) return n;
+    } else if (k <= TG_DOWN_LADDER && ticker(e.flags) == 0) {
+        // Straight-line form of the up_ladder / down_ladder tick (opts:160-189 + impl:290-359).  playerx never changes,
+        // so the two probes of every tick look at fixed columns: a column profile per probe (bit r = the probe's
+        // cells of padded row r) turns them into register bit tests -- lad: LADDER at x -+ 12 (impl:240-257),
+        // blk: anything but OPEN at x -+ 10, closed doors included (impl:283-288; doors cannot move during the option).
+        // While the ladder probe holds and the player cannot fall, tick(UP/DOWN) is: count the action, move by noisy(),
+        // pick up.  Any other situation leaves the loop *before* the tick and the general loop below takes over from the
+        // same state (the terminating NOP tick included).  Building the profiles costs about two general ticks; ladder
+        // options last 17 ticks on average, and they are the long pole of small batches (4096 envs: 50.6 -> 39.8 us).
+        const bool up = (k == TG_UP_LADDER);
+        const int c0 = pad_cell(e.px - 12), c1 = pad_cell(e.px + 12), ca = pad_cell(e.px - 10), cb = pad_cell(e.px + 10);
+        uint32_t lad = 0, blk = 0;
+        const int nrows = L.ch + 2 * PAD;
+        for (int r = 0; r < nrows; r++) {
+            const uint32_t ml = L.row_ladder[r], mn = L.row_nonopen[r] | door_bits(L, e.flags, r);
+            lad |= (((ml >> c0) | (ml >> c1)) & 1u) << r;
+            blk |= (((mn >> ca) | (mn >> cb)) & 1u) << r;
+        }
+        bool near_item = false;                     // an item in this column's pick-up range (impl:350-354)?  else no pickups at all
+#pragma unroll
+        for (int i = 0; i < NI; i++) near_item |= (i < L.n_items) && abs(e.px - (e.ix[i] + S / 2)) < 24;
+        for (;;) {
+            const int py = e.py;
+            const int r1 = pad_cell(py);
+            const uint32_t probe = up ? ((lad >> pad_cell(py - 4)) | (lad >> r1) | (lad >> pad_cell(py + 44)))
+                                      : ((lad >> r1) | (lad >> min(r1 + 1, pad_cell(py + 51))) | (lad >> pad_cell(py + 51)));
+            if (!(probe & 1u) || (up && py <= 1)) break;                        // opts:168-173 / 184-189: the NOP tick follows
+            if ((((blk >> r1) | (blk >> pad_cell(py + 50))) & 1u) == 0u) break;   // can_fall: the general tick
+            e.py = py + noisy<TAPE>(e, up);
+            n++;
+            if (near_item) pickups(e, L);
+            if (n >= TG_TICK_CAP) { e.total_actions += n; e.flags |= 1u << F_ERROR; return n; }
+        }
+        e.total_actions += n;
     }
     do {
         int act, lad = -1;
