@@ -185,3 +185,50 @@ class CBatch:
             bolts=[int(v) for v in s["bolts"][i]], items=[tuple(int(v) for v in it) for it in s["items"][i]],
             bag=[int(v) for v in s["bag"][i] if v >= 0], total_actions=int(s["misc"][i, 2]),
             handles_pt=[int(v) for v in self.handles_pt()[i]])
+
+
+class ShardedCBatch:
+    """``n`` envs split into contiguous sub-batches stepped by one Python thread each (ctypes releases the GIL;
+    every env owns its Philox stream keyed by the global env id, so the split is invisible).  Same interface
+    as ``CBatch`` for what the full-size parity tests use: 1,048,576 envs x 130 steps take seconds."""
+
+    def __init__(self, level: CLevel, n, first_env_id=0, seed=0, max_episode_steps=0, auto_reset=False, threads=None):
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        self.level, self.n = level, int(n)
+        threads = max(1, min(threads or os.cpu_count() or 1, (self.n + 4095) // 4096))
+        cuts = [self.n * k // threads for k in range(threads + 1)]
+        self.ranges = [(cuts[k], cuts[k + 1]) for k in range(threads) if cuts[k + 1] > cuts[k]]
+        self.parts = [CBatch(level, hi - lo, first_env_id + lo, seed, max_episode_steps, auto_reset) for lo, hi in self.ranges]
+        self.pool = ThreadPoolExecutor(len(self.parts))
+
+    def _map(self, fn):
+        return list(self.pool.map(fn, range(len(self.parts))))
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        return np.concatenate(self._map(lambda k: self.parts[k].reset(None if m is None else m[self.ranges[k][0]:self.ranges[k][1]])))
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        outs = self._map(lambda k: self.parts[k].step(a[self.ranges[k][0]:self.ranges[k][1]]))
+        return tuple(np.concatenate([o[j] for o in outs]) for j in range(5))
+
+    def mask(self):
+        return np.concatenate(self._map(lambda k: self.parts[k].mask()))
+
+    def stats(self):
+        return np.sum(self._map(lambda k: self.parts[k].stats()), axis=0)
+
+    def state(self):
+        sts = self._map(lambda k: self.parts[k].state())
+        return {key: np.concatenate([s[key] for s in sts]) for key in sts[0]}
+
+    def handles_pt(self):
+        return np.concatenate(self._map(lambda k: self.parts[k].handles_pt()))
+
+    def snapshot(self, i=0):
+        for (lo, hi), p in zip(self.ranges, self.parts):
+            if lo <= i < hi:
+                return p.snapshot(i - lo)
+        raise IndexError(i)
