@@ -84,6 +84,24 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+# ----------------------------------------------------------------------------- steady state
+def desynchronise(env, torch, new_actions, max_episode_steps=MAX_EPISODE_STEPS, seed=99):
+    """Brings a freshly created batch to the steady state of the workload, outside any timed region: one episode
+    length of steps, then every env's episode age is redrawn uniformly in [0, max_episode_steps) (tg_set_state),
+    then one more episode length so that every env has been reset at its own time.  From then on about 1 % of
+    the envs hit the time limit in every step (instead of all of them together every 100th step)."""
+    n = env.num_envs
+    for _ in range(max_episode_steps):
+        env.step_raw(new_actions())
+    st = env.get_state()
+    g = torch.Generator(device=env.device).manual_seed(seed)
+    acct = st["acct"]
+    acct[:, 1] = torch.randint(0, max_episode_steps, (n,), generator=g, device=env.device, dtype=torch.int64)
+    env.set_state({"acct": acct})
+    for _ in range(max_episode_steps + 10):
+        env.step_raw(new_actions())
+
+
 # ----------------------------------------------------------------------------- CPU baselines
 def _py_worker(args):
     seed, seconds = args

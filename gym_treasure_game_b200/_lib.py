@@ -59,6 +59,7 @@ _SIGNATURES = {
     "tg_obs_dim": (C.c_int32, [C.c_void_p]),
     "tg_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tg_step": (C.c_int, [C.c_void_p] * 8),
+    "tg_bind_obs": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tg_step_host": (C.c_int, [C.c_void_p] * 7),
     "tg_step_host_sparse": (C.c_int, [C.c_void_p] * 7),
     "tg_available_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -77,6 +78,7 @@ _SIGNATURES = {
     "tg_launch_count": (C.c_int64, [C.c_void_p]),
     "tg_host_traffic": (None, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "tg_debug_phase_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tg_debug_set_step_tile": (C.c_int, [C.c_void_p, C.c_int32]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

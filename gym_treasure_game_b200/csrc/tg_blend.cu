@@ -249,12 +249,13 @@ static size_t blend_smem_bytes(int W) { return (((size_t)BLEND_ROWS * W * 3 + 12
 
 cudaError_t launch_blend(const BatchView &B, const RenderView &R, int64_t first, int64_t n_surfaces, int64_t per,
                          uint8_t *surfaces, int alpha_objs, int alpha_player, cudaStream_t s) {
-    static size_t allowed = 48 * 1024;
+    static size_t allowed[MAX_DEVICES] = {};                       // per device: function attributes are per device
     const size_t smem = blend_smem_bytes(R.frame_w);
-    if (smem > allowed) {
+    const int dslot = device_slot();
+    if (smem > 48 * 1024 && smem > allowed[dslot]) {
         cudaError_t e = cudaFuncSetAttribute(tg_blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        allowed = smem;
+        allowed[dslot] = smem;
     }
     const unsigned bands = (unsigned)((R.frame_h + BLEND_ROWS - 1) / BLEND_ROWS);
     for (int64_t s0 = 0; s0 < n_surfaces; s0 += 32768) {           // gridDim.y limit

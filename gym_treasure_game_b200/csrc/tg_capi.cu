@@ -66,6 +66,12 @@ struct tg_env {
     // device-side staging for tg_step_host (owned through `allocs`)
     int32_t *s_actions = nullptr; float *s_obs = nullptr; float *s_reward = nullptr;
     uint8_t *s_done = nullptr; uint8_t *s_ran = nullptr;
+    // Observation bookkeeping: the step kernel only writes the observation rows of envs whose state changed (an option
+    // that cannot run leaves its env untouched, opt:22-23).  `obs_sync` is the device buffer known to hold every env's
+    // current row (NULL: none); it is trusted when it is the caller's bound buffer (tg_bind_obs) or the library's own
+    // staging buffer.  Any other `obs` argument gets every row written (tg_obs_kernel after the step kernel).
+    const float *obs_bound = nullptr, *obs_sync = nullptr;
+    int step_tile = 0;                 // envs per step-kernel CTA; 0 = chosen by the launcher (TG_STEP_TILE / tg_debug_set_step_tile)
     int64_t launches = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;   // copied by the *_host entry points
     // tg_step_host pipeline: step kernel of chunk c+1 overlaps the device->host copies of chunk c
@@ -201,6 +207,15 @@ extern "C" int tg_level_create(const uint8_t *tiles, int32_t cw, int32_t ch, con
         b.trig_dst[t] = (uint8_t)(obj_of[tr.dst_kind][tr.dst_index] | (tr.dst_value ? 128 : 0));
     }
     b.n_trigs = (uint8_t)n_trigs;
+    {   // grouped by (source object, value), file order inside a group
+        int pos = 0;
+        for (int key = 0; key < 2 * TG_MAX_OBJECTS; key++) {
+            b.trig_begin[key] = (uint8_t)pos;
+            const uint8_t src = (uint8_t)((key >> 1) | ((key & 1) ? 128 : 0));
+            for (int t = 0; t < n_trigs; t++) if (b.trig_src[t] == src) b.trig_list[pos++] = b.trig_dst[t];
+        }
+        for (int key = 2 * TG_MAX_OBJECTS; key < 2 * TG_MAX_OBJECTS + 8; key++) b.trig_begin[key] = (uint8_t)pos;
+    }
     // row bit masks (door cells read as OPEN here; closed doors are OR-ed in from door_lut at run time)
     for (int r = 0; r < TSTRIDE; r++)
         for (int c = 0; c < TSTRIDE; c++) {
@@ -208,9 +223,9 @@ extern "C" int tg_level_create(const uint8_t *tiles, int32_t cw, int32_t ch, con
             if (code & TC_STATIC_OBJ) b.row_static_obj[r] |= 1u << c;
             if (code & TC_HAS_DOOR) continue;
             const int t = code & 3;
-            if (t != T_OPEN) b.row_nonopen[r] |= 1u << c;
+            if (t != T_OPEN) { b.row_nonopen[r] |= 1u << c; b.col_nonopen[c] |= 1u << r; }
             if (t == T_WALL) b.row_solid[r] |= 1u << c;
-            if (t == T_LADDER) b.row_ladder[r] |= 1u << c;
+            if (t == T_LADDER) { b.row_ladder[r] |= 1u << c; b.col_ladder[c] |= 1u << r; }
         }
     {
         int n_rows = 0;
@@ -297,6 +312,7 @@ extern "C" int tg_create(const tg_level *const *levels, int32_t n_levels, const 
     tg_env *e = new (std::nothrow) tg_env();
     if (!e) return fail(TG_ERR_NOMEM, "out of host memory");
     e->device = device; e->n_levels = n_levels;
+    { const char *v = getenv("TG_STEP_TILE"); e->step_tile = v ? atoi(v) : 0; }
     BatchView &B = e->B;
     B.n = num_envs; B.first_env_id = first_env_id; B.n_levels = n_levels;
     B.r_begin = 0; B.r_count = num_envs;
@@ -325,6 +341,13 @@ extern "C" int tg_create(const tg_level *const *levels, int32_t n_levels, const 
     B.levels = d_levels;
     CUE(dev_alloc(e, &B.core, (size_t)num_envs));
     CUE(dev_alloc(e, &B.acct, (size_t)num_envs));
+    CUE(dev_alloc(e, &B.plan, (size_t)num_envs + 4));       // + 4: the step kernel's 16-byte loads never leave the allocation
+    CUE(dev_alloc(e, &B.ep_start, (size_t)num_envs + 4));
+    CUE(cudaMemset(B.plan, 0, sizeof(uint64_t) * ((size_t)num_envs + 4)));
+    CUE(cudaMemset(B.ep_start, 0, sizeof(uint32_t) * ((size_t)num_envs + 4)));
+    CUE(dev_alloc(e, &B.step_counter, (size_t)4));
+    CUE(cudaMemset(B.step_counter, 0, 4 * sizeof(uint32_t)));
+    B.advance = 1;
     CUE(cudaMemset(B.core, 0, sizeof(uint4) * (size_t)num_envs));
     CUE(cudaMemset(B.acct, 0, sizeof(uint4) * (size_t)num_envs));
     if (e->ni > 2) { CUE(dev_alloc(e, &B.items23, (size_t)num_envs)); CUE(cudaMemset(B.items23, 0, sizeof(uint2) * (size_t)num_envs)); }
@@ -400,16 +423,32 @@ extern "C" int tg_reset(tg_env *env, const uint8_t *mask, float *obs, void *stre
     CU(launch_reset(env->B, env->ni, mask, obs, (cudaStream_t)stream));
     env->launches++;
     env->sp_primed = false;
+    env->obs_sync = obs;                 // the reset kernel writes every env's row (NULL: no buffer is current)
     return TG_OK;
+}
+
+static bool obs_is_current(const tg_env *env, const float *obs) {
+    return obs && obs == env->obs_sync && (obs == env->obs_bound || obs == env->s_obs);
 }
 
 extern "C" int tg_step(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done, uint8_t *ran,
                        uint16_t *avail, void *stream) {
     if (!env || !actions) return fail(TG_ERR_ARG, "null argument");
     DeviceGuard guard(env->device);
-    CU(launch_step(env->B, env->ni, actions, obs, reward, done, ran, avail, (cudaStream_t)stream));
+    CU(launch_step(env->B, env->ni, env->step_tile, actions, obs, reward, done, ran, avail, (cudaStream_t)stream));
     env->launches++;
+    if (obs && !obs_is_current(env, obs)) {        // not the bound buffer with last step's rows in it: every row
+        CU(launch_obs(env->B, env->ni, obs, (cudaStream_t)stream));
+        env->launches++;
+    }
+    env->obs_sync = obs;
     env->sp_primed = false;
+    return TG_OK;
+}
+
+extern "C" int tg_bind_obs(tg_env *env, float *obs) {
+    if (!env) return fail(TG_ERR_ARG, "null env");
+    env->obs_bound = obs;
     return TG_OK;
 }
 
@@ -446,14 +485,16 @@ extern "C" int tg_step_host(tg_env *env, const int32_t *actions, float *obs, flo
     env->h2d_bytes += n * (int64_t)sizeof(int32_t);
     env->d2h_bytes += n * ((obs ? (int64_t)od * 4 : 0) + (reward ? 4 : 0) + (done ? 1 : 0) + (ran ? 1 : 0));
     const int64_t per = ((n + chunks - 1) / chunks + 2047) / 2048 * 2048;      // tile-aligned chunk size
-    for (int c = 0; c < chunks; c++) {
+    const int used_chunks = (int)((n + per - 1) / per);
+    const bool obs_full = obs && !obs_is_current(env, env->s_obs);             // the staging buffer lacks the rows of idle envs
+    for (int c = 0; c < used_chunks; c++) {
         const int64_t lo = (int64_t)c * per, cnt = (lo + per <= n) ? per : n - lo;
-        if (cnt <= 0) break;
         BatchView V = env->B;
-        V.r_begin = lo; V.r_count = cnt;
-        CU(launch_step(V, env->ni, env->s_actions, obs ? env->s_obs : nullptr, reward ? env->s_reward : nullptr,
+        V.r_begin = lo; V.r_count = cnt; V.advance = (c == used_chunks - 1) ? 1 : 0;
+        CU(launch_step(V, env->ni, env->step_tile, env->s_actions, obs ? env->s_obs : nullptr, reward ? env->s_reward : nullptr,
                        done ? env->s_done : nullptr, ran ? env->s_ran : nullptr, nullptr, s));
         env->launches++;
+        if (obs_full) { CU(launch_obs(V, env->ni, env->s_obs, s)); env->launches++; }
         cudaStream_t cs = s;
         if (chunks > 1) {
             CU(cudaEventRecord(env->ev_chunk[c], s));
@@ -470,6 +511,7 @@ extern "C" int tg_step_host(tg_env *env, const int32_t *actions, float *obs, flo
         CU(cudaStreamWaitEvent(s, env->ev_join, 0));
     }
     CU(cudaStreamSynchronize(s));
+    env->obs_sync = obs ? env->s_obs : nullptr;
     // the caller's arrays now hold every env's outputs: tg_step_host_sparse may patch them from here on
     env->sp_primed = obs && reward && done && ran;
     env->sp_dense_flags = true;
@@ -556,13 +598,14 @@ extern "C" int tg_step_host_sparse(tg_env *env, const int32_t *actions, float *o
     env->h2d_bytes += n * (int64_t)sizeof(int32_t);
     CU(cudaMemsetAsync(env->sp_dcount, 0, 8 * sizeof(uint32_t), s));
     int used = 0;
-    for (int c = 0; c < chunks; c++) {
+    const int used_chunks = (int)((n + per - 1) / per);
+    env->obs_sync = nullptr;                         // only records leave the device: no device buffer follows this step
+    for (int c = 0; c < used_chunks; c++) {
         const int64_t lo = (int64_t)c * per, cnt = (lo + per <= n) ? per : n - lo;
-        if (cnt <= 0) break;
         BatchView V = env->B;
-        V.r_begin = lo; V.r_count = cnt;
+        V.r_begin = lo; V.r_count = cnt; V.advance = (c == used_chunks - 1) ? 1 : 0;
         V.sp_count = env->sp_dcount + c; V.sp_recs = env->sp_drecs + (size_t)lo * words; V.sp_words = words;
-        CU(launch_step(V, env->ni, env->s_actions, nullptr, nullptr, nullptr, nullptr, nullptr, s));
+        CU(launch_step(V, env->ni, env->step_tile, env->s_actions, nullptr, nullptr, nullptr, nullptr, nullptr, s));
         env->launches++;
         CU(cudaEventRecord(env->ev_chunk[c], s));
         CU(cudaStreamWaitEvent(env->side, env->ev_chunk[c], 0));
@@ -625,6 +668,7 @@ extern "C" int tg_render(tg_env *env, int64_t first, int64_t count, uint8_t *fra
     if (!env || !frames) return fail(TG_ERR_ARG, "null argument");
     if (!env->has_render) return fail(TG_ERR_STATE, "render needs tg_level_set_sprites on every level (and equal grid sizes)");
     if (first < 0 || count < 0 || first + count > env->B.n) return fail(TG_ERR_ARG, "frame range outside the batch");
+    if (reinterpret_cast<uintptr_t>(frames) & 15u) return fail(TG_ERR_ARG, "frames must be 16-byte aligned (bulk stores)");
     if (count == 0) return TG_OK;
     DeviceGuard guard(env->device);
     CU(launch_render(env->B, env->R, first, count, frames, (cudaStream_t)stream));
@@ -680,6 +724,7 @@ extern "C" int tg_set_state(tg_env *env, const tg_state_view *in, void *stream) 
     CU(launch_set_state(env->B, *in, (cudaStream_t)stream));
     env->launches++;
     env->sp_primed = false;
+    env->obs_sync = nullptr;
     return TG_OK;
 }
 
@@ -689,6 +734,7 @@ extern "C" int tg_primitive_step(tg_env *env, const int32_t *actions, float *obs
     CU(launch_primitive(env->B, env->ni, actions, obs, reward, done, (cudaStream_t)stream));
     env->launches++;
     env->sp_primed = false;
+    env->obs_sync = obs;                 // every env's row is written
     return TG_OK;
 }
 
@@ -698,6 +744,7 @@ extern "C" int tg_init_with_state(tg_env *env, const double *states, const uint8
     CU(launch_init_with_state(env->B, env->ni, states, mask, (cudaStream_t)stream));
     env->launches++;
     env->sp_primed = false;
+    env->obs_sync = nullptr;
     return TG_OK;
 }
 
@@ -714,6 +761,13 @@ extern "C" int tg_set_draw_tape(tg_env *env, const double *tape, const int64_t *
 extern "C" int tg_debug_phase_buffer(tg_env *env, uint64_t *stamps) {
     if (!env) return fail(TG_ERR_ARG, "null env");
     env->B.phase_ts = reinterpret_cast<unsigned long long *>(stamps);
+    return TG_OK;
+}
+
+extern "C" int tg_debug_set_step_tile(tg_env *env, int32_t tile) {
+    if (!env) return fail(TG_ERR_ARG, "null env");
+    if (tile != 0 && (tile < 32 || tile > 4096)) return fail(TG_ERR_ARG, "tile must be 0 (automatic) or 32..4096");
+    env->step_tile = tile;
     return TG_OK;
 }
 

@@ -29,6 +29,7 @@ struct Env {
     uint32_t d0, w0, w1, w2, w3;    // draw index at the start of this API call, cached Philox block
     uint32_t key0, key1, id_lo, id_hi;
     const double *tape;             // parity mode: this env's slice of the draw tape
+    uint32_t tape_len;              // ... and its length: a draw past the end flags the env (F_ERROR) and reads 0
     // row-mask cache for the probes every tick makes (valid while the probed pair of rows is the one in the key and the doors
     // do not move): m_fall = non-open cells of the rows of y and y+50, m_side = solid cells of the
     // rows of y+4 and y+44; bit = padded column.  A walk never changes y, so its ticks only shift/test.
@@ -54,6 +55,17 @@ __device__ __forceinline__ uint32_t bag_items(uint32_t f) {
     return m;
 }
 
+// ---- packed state words -----------------------------------------------------
+__device__ __forceinline__ uint32_t pack_xy(int x, int y) { return ((uint32_t)x & 0xFFFFu) | ((uint32_t)y << 16); }
+// core.x = playerx (12 bits, 0 <= x < 26*48) | sticky handle flags (4 bits) | playery << 16
+__device__ __forceinline__ uint32_t pack_player(int px, int py, uint32_t sticky) {
+    return ((uint32_t)px & 0xFFFu) | ((sticky & 15u) << 12) | ((uint32_t)py << 16);
+}
+__device__ __forceinline__ int core_px(uint32_t v) { return (int)(v & 0xFFFu); }
+__device__ __forceinline__ uint32_t core_sticky(uint32_t v) { return (v >> 12) & 15u; }
+__device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xFFFFu); }
+__device__ __forceinline__ int hi16(uint32_t v) { return (int)(int16_t)(v >> 16); }
+
 // ---------------------------------------------------------------------------
 // RNG: Philox4x32-10, four 32-bit uniforms per block (u = word / 2^32).
 // ctr = (d0, j >> 2, env_id_lo, env_id_hi), key = (seed_lo, seed_hi); word = j & 3 (see draw_k)
@@ -70,6 +82,29 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     }
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
+// Blocks (c0, b) and (c0, b + 1) side by side: two independent dependency chains for the fast-forward loop of the walkers
+__device__ __forceinline__ void philox4x32_10_x2(uint32_t c0, uint32_t b, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                                 uint32_t &x0, uint32_t &x1, uint32_t &x2, uint32_t &x3,
+                                                 uint32_t &y0, uint32_t &y1, uint32_t &y2, uint32_t &y3) {
+    uint32_t a0 = c0, a1 = b, a2 = c2, a3 = c3, d0 = c0, d1 = b + 1u, d2 = c2, d3 = c3;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t ah0 = __umulhi(0xD2511F53u, a0), al0 = 0xD2511F53u * a0, ah1 = __umulhi(0xCD9E8D57u, a2), al1 = 0xCD9E8D57u * a2;
+        const uint32_t dh0 = __umulhi(0xD2511F53u, d0), dl0 = 0xD2511F53u * d0, dh1 = __umulhi(0xCD9E8D57u, d2), dl1 = 0xCD9E8D57u * d2;
+        a0 = ah1 ^ a1 ^ k0; a1 = al1; a2 = ah0 ^ a3 ^ k1; a3 = al0;
+        d0 = dh1 ^ d1 ^ k0; d1 = dl1; d2 = dh0 ^ d3 ^ k1; d3 = dl0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    x0 = a0; x1 = a1; x2 = a2; x3 = a3; y0 = d0; y1 = d1; y2 = d2; y3 = d3;
+}
+// One copy of the block function per kernel, called from every draw site: inlined at each of the ~10 sites it was
+// 14 KB of a 118 KB kernel body whose warps (different option classes side by side) kept missing the 32 KB
+// instruction cache (profiles/r02_step_v13_ncu.txt: no-instruction 5.0 stalled warps per issue).
+static __device__ __noinline__ uint4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    uint4 o;
+    philox4x32_10(c0, c1, c2, c3, k0, k1, o.x, o.y, o.z, o.w);
+    return o;
+}
 
 // One uniform draw as the integer k with u = k / 2^53.  Tape mode: k is the recorded CPython double times
 // 2^53 (exact: MT outputs are multiples of 2^-53).  Philox mode: one 32-bit word per draw, u = w / 2^32,
@@ -84,14 +119,20 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 template <int NI>
 __device__ __forceinline__ uint32_t draw_w(Env<NI> &e) {           // Philox mode: the 32-bit word of the next draw
     uint32_t j = e.draws++ - e.d0;
-    if ((j & 3u) == 0u)
-        philox4x32_10(e.d0, j >> 2, e.id_lo, e.id_hi, e.key0, e.key1, e.w0, e.w1, e.w2, e.w3);
+    if ((j & 3u) == 0u) {
+        const uint4 o = philox_block(e.d0, j >> 2, e.id_lo, e.id_hi, e.key0, e.key1);
+        e.w0 = o.x; e.w1 = o.y; e.w2 = o.z; e.w3 = o.w;
+    }
     const uint32_t lo = (j & 1u) ? e.w1 : e.w0, hi = (j & 1u) ? e.w3 : e.w2;
     return (j & 2u) ? hi : lo;
 }
 template <bool TAPE, int NI>
 __device__ __forceinline__ uint64_t draw_k(Env<NI> &e) {
-    if (TAPE) return (uint64_t)__double2ull_rz(e.tape[e.draws++] * 9007199254740992.0);
+    if (TAPE) {
+        const uint32_t j = e.draws++;
+        if (j >= e.tape_len) { e.flags |= 1u << F_ERROR; return 0ull; }     // tape exhausted: never read out of bounds
+        return (uint64_t)__double2ull_rz(e.tape[j] * 9007199254740992.0);
+    }
     return (uint64_t)draw_w(e) << 21;
 }
 __device__ __forceinline__ double k_to_unit(uint64_t k) { return (double)k * (1.0 / 9007199254740992.0); }   // exact
@@ -117,6 +158,8 @@ __device__ __forceinline__ double handle_angle(bool up, double u) {
 // which adds < 0.016 to the quotient; the largest fractional part is 47/48 = 0.979), one IMAD + one shift.
 static_assert(S == 48 && TSTRIDE == 32, "pad_cell's multiply-shift division is derived for 48-px cells and a 32-cell table");
 __device__ __forceinline__ int pad_cell(int v) { return (int)(((unsigned)(v + PAD * S) * 1366u) >> 16); }
+// v mod 48 for v >= -PAD*S
+__device__ __forceinline__ int mod48(int v) { return v + PAD * S - S * pad_cell(v); }
 __device__ __forceinline__ int pad_idx(int c) { return min(max(c + PAD, 0), TSTRIDE - 1); }
 
 // effective type of the cell with padded indices (ixp, iyp)    impl:218-225 + objs:246-253
@@ -262,31 +305,42 @@ __device__ __forceinline__ bool apply_val(Env<NI> &e, const LevelBlob &L, int o,
 // set of objects whose previously_triggered flag is raised: those on the DFS stack plus the handles that
 // init_with_state left flagged (impl:473, Env::sticky); a flag is lowered when its object's own
 // process_trigger returns (objs:94), which is also how a sticky flag eventually clears.
+// The stack lives in registers: an object is on it at most once (its flag in `pt` blocks re-entry), so a level is the
+// object (4 bits; its value is the one it holds now) and the position in its trigger list (8 bits).
 template <bool TAPE, int NI>
 __device__ __forceinline__ void trigger_dfs(Env<NI> &e, const LevelBlob &L, int o0, bool v0) {
-    uint8_t st_src[TG_MAX_OBJECTS], st_t[TG_MAX_OBJECTS];
+    static_assert(TG_MAX_OBJECTS <= 16 && TG_MAX_TRIGGERS < 256, "trigger_dfs packs its stack into three 64-bit words");
+    uint64_t st_obj = 0, st_t0 = 0, st_t1 = 0;                    // level l: object = nibble l, list position = byte l (st_t0: levels 0-7)
     int sp = 0;
     uint32_t pt = 0;
     for (int h = 0; h < L.n_handles; h++) if ((e.sticky >> h) & 1u) pt |= 1u << L.handle_obj[h];
     pt |= 1u << o0;
-    st_src[0] = (uint8_t)(o0 | (v0 ? 128 : 0)); st_t[0] = 0; sp = 1;
+    auto set_t = [&](int l, uint32_t t) {
+        const int sh = 8 * (l & 7);
+        if (l < 8) st_t0 = (st_t0 & ~(0xFFull << sh)) | ((uint64_t)t << sh); else st_t1 = (st_t1 & ~(0xFFull << sh)) | ((uint64_t)t << sh);
+    };
+    st_obj = (uint64_t)o0; set_t(0, L.trig_begin[2 * o0 + (v0 ? 1 : 0)]); sp = 1;
     while (sp > 0) {
-        int src = st_src[sp - 1], t = st_t[sp - 1];
+        const int l = sp - 1;
+        const int o = (int)((st_obj >> (4 * l)) & 15ull);
+        uint32_t t = (uint32_t)(((l < 8 ? st_t0 : st_t1) >> (8 * (l & 7))) & 0xFFull);
+        const uint32_t tend = L.trig_begin[2 * o + (obj_value(L, e.flags, o) ? 1 : 0) + 1];
         bool pushed = false;
-        while (t < L.n_trigs) {
-            int cur = t++;
-            if (L.trig_src[cur] != src) continue;
-            int dst = L.trig_dst[cur] & 127; bool dv = L.trig_dst[cur] >> 7;
+        while (t < tend) {
+            const int ent = L.trig_list[t++];
+            const int dst = ent & 127; const bool dv = ent >> 7;
             if (pt & (1u << dst)) continue;                       // objs:84 / :91
             if (apply_val<TAPE>(e, L, dst, dv)) {
-                st_t[sp - 1] = (uint8_t)t;
+                set_t(l, t);
                 pt |= 1u << dst;
-                st_src[sp] = (uint8_t)(dst | (dv ? 128 : 0)); st_t[sp] = 0; sp++;
+                st_obj = (st_obj & ~(15ull << (4 * sp))) | ((uint64_t)dst << (4 * sp));
+                set_t(sp, L.trig_begin[2 * dst + (dv ? 1 : 0)]);
+                sp++;
                 pushed = true;
                 break;
             }
         }
-        if (!pushed) { pt &= ~(1u << (src & 127)); sp--; }         // objs:94
+        if (!pushed) { pt &= ~(1u << o); sp--; }                   // objs:94
     }
     uint32_t sticky = 0;
     for (int h = 0; h < L.n_handles; h++) if ((pt >> L.handle_obj[h]) & 1u) sticky |= 1u << h;
@@ -351,6 +405,47 @@ __device__ __forceinline__ int noisy_from_k(uint64_t k, bool negative) {
 }
 // For k = w << 21 (Philox mode) the same function in 32-bit arithmetic: q = w << 20, k & q & 1 = 0, m = w << 20.
 __device__ __forceinline__ int noisy_r_from_w(uint32_t w) { return (int)(w > (1u << 30)) + (int)(w >= (3u << 30)); }
+// The cached block holds the word of the next draw (refilled at a block boundary): for the straight-line loops, which
+// then take their words with noisy_cached / consume_block.
+template <int NI>
+__device__ __forceinline__ void ensure_block(Env<NI> &e) {
+    const uint32_t j = e.draws - e.d0;
+    if ((j & 3u) == 0u) {
+        const uint4 o = philox_block(e.d0, j >> 2, e.id_lo, e.id_hi, e.key0, e.key1);
+        e.w0 = o.x; e.w1 = o.y; e.w2 = o.z; e.w3 = o.w;
+    }
+}
+// Up to `limit` unchecked ticks of noisy(-4) (neg) / noisy(+4) from the words left in the cached block, branch-free.
+// A tick may run when it starts inside the safe stretch, i.e. when the distance moved before it is <= D; the moves
+// are positive (2, 3 or 4 px), so these are comparisons of the prefix sums with D.  Returns the number of ticks (>= 1
+// when D >= 0), `moved` = pixels moved (absolute value); advances the draw index.
+template <int NI>
+__device__ __forceinline__ int consume_block(Env<NI> &e, bool neg, int D, int limit, int &moved) {
+    const uint32_t a = (e.draws - e.d0) & 3u;
+    uint32_t w0 = e.w0, w1 = e.w1, w2 = e.w2, w3 = e.w3;
+    if (a & 1u) { w0 = w1; w1 = w2; w2 = w3; }
+    if (a & 2u) { w0 = w2; w1 = w3; }
+    const int avail = min(4 - (int)a, limit);
+    const int base = neg ? 4 : 2, sg = neg ? -1 : 1;                               // |noisy(-4)| = 4 - r, noisy(+4) = 2 + r
+    const int p1 = base + sg * noisy_r_from_w(w0), p2 = p1 + base + sg * noisy_r_from_w(w1),
+              p3 = p2 + base + sg * noisy_r_from_w(w2), p4 = p3 + base + sg * noisy_r_from_w(w3);
+    const bool ok0 = avail > 0 && D >= 0, ok1 = ok0 && avail > 1 && p1 <= D, ok2 = ok1 && avail > 2 && p2 <= D,
+               ok3 = ok2 && avail > 3 && p3 <= D;
+    const int u = (int)ok0 + (int)ok1 + (int)ok2 + (int)ok3;
+    moved = ok3 ? p4 : ok2 ? p3 : ok1 ? p2 : ok0 ? p1 : 0;
+    e.draws += (uint32_t)u;
+    return u;
+}
+
+// noisy() for a caller that has just refilled the block at a block boundary (the straight-line option loops): the
+// word of the next draw comes from the cached block, no refill check
+template <bool TAPE, int NI>
+__device__ __forceinline__ int noisy_cached(Env<NI> &e, bool negative) {
+    if (TAPE) return noisy_from_k(draw_k<true>(e), negative);
+    const uint32_t j = e.draws++ - e.d0;
+    const uint32_t lo = (j & 1u) ? e.w1 : e.w0, hi = (j & 1u) ? e.w3 : e.w2;
+    return (negative ? -4 : 2) + noisy_r_from_w((j & 2u) ? hi : lo);
+}
 template <bool TAPE, int NI>
 __device__ __forceinline__ int noisy(Env<NI> &e, bool negative) {
     if (TAPE) return noisy_from_k(draw_k<true>(e), negative);
@@ -378,7 +473,9 @@ __device__ __forceinline__ void pickups(Env<NI> &e, const LevelBlob &L) {
 
 // `ladder_ok` >= 0 passes the ladder probe the option policy has just evaluated for UP / DOWN (same state, same
 // result as impl:298 / :302 would compute again); -1 = evaluate here.
-template <bool TAPE, int NI>
+// INTERACT_OK = false leaves out the INTERACT branch (trigger graph, handle angles: the step kernel runs the interact
+// option out of line, interact_option_mem below, to keep that code out of its hot instruction footprint).
+template <bool TAPE, int NI, bool INTERACT_OK = true>
 __device__ __forceinline__ void tick(Env<NI> &e, const LevelBlob &L, int act, int ladder_ok = -1) {
     int xd = 0, yd = 0;
     e.total_actions++;
@@ -397,7 +494,7 @@ __device__ __forceinline__ void tick(Env<NI> &e, const LevelBlob &L, int act, in
     } else if (act == A_JUMP) {
         if (!ladder_probe(L, e.px, e.py, false) && up_clear_m(e, L))
             e.flags = set_ticker(e.flags, draw_k<TAPE>(e) > (1ull << 51) ? 23 : 22);   // impl:316-319: random() > 0.25
-    } else if (act == A_INTERACT) {
+    } else if (INTERACT_OK && act == A_INTERACT) {
         interact<TAPE>(e, L);
         row_cache_drop(e);           // doors may have moved
     }
@@ -496,8 +593,8 @@ __device__ __forceinline__ bool option_setup(const Env<NI> &e, const LevelBlob &
     switch (k) {
     case TG_GO_LEFT:  return walk_setup(e, L, -1, tcx);
     case TG_GO_RIGHT: return walk_setup(e, L, +1, tcx);
-    case TG_UP_LADDER:   return can_go_up(L, f, e.px, e.py);          // opts:165-166
-    case TG_DOWN_LADDER: return can_go_down(L, f, e.px, e.py);        // opts:181-182
+    case TG_UP_LADDER:   return ladder_probe(L, e.px, e.py, true);    // opts:165-166 (impl:240-250)
+    case TG_DOWN_LADDER: return ladder_probe(L, e.px, e.py, false);   // opts:181-182 (impl:252-257)
     case TG_INTERACT: {                                               // opts:446-455
         bool r = false;
         for (int i = 0; i < L.n_handles; i++)
@@ -569,76 +666,186 @@ __device__ __forceinline__ int walk_safe_bound(const Env<NI> &e, const LevelBlob
     return bound;
 }
 
-// Runs option k (already known to be runnable, target column tcx from option_setup) to
-// termination.  Returns the number of primitive ticks; reward = -ticks - 4*[jump option]
-// (impl:15-16,356-359).
+// The middle of a drop / jump option: LEFT / RIGHT ticks until the player is within 4 px of the target column
+// (opts:239-244 / 305-314; a jump turns round while it stands blocked, opts:309-312).  This is tick(LEFT / RIGHT)
+// (impl:305-313, 331-354) without the action switch: side probe, noisy() from the cached block, the jump ticker or the
+// fall, pick-ups only when an item shares the column range.  A lane runs these ticks on its own (drops and jumps are
+// 0.04 % of the steps under random actions but the longest serial chains of a tile), so the instructions per tick are
+// what matters.  Returns false when the tick cap was hit.
 template <bool TAPE, int NI>
-__device__ __forceinline__ int run_option_to_end(Env<NI> &e, const LevelBlob &L, int k, int tcx) {
+__device__ __forceinline__ bool move_until_aligned(Env<NI> &e, const LevelBlob &L, bool jump, int s, int tpx, int &n) {
+    while (abs(tpx - e.px) >= 4) {
+        const bool blocked = !side_free_m(e, L, e.px + 16 * s);
+        int dir = s;
+        if (jump && blocked && !can_fall_m(e, L)) dir = -s;
+        const bool go = (dir == s) ? !blocked : side_free_m(e, L, e.px + 16 * dir);
+        e.total_actions++;
+        int xd = 0, yd = 0;
+        if (go) {
+            if (!TAPE) ensure_block(e);
+            xd = noisy_cached<TAPE>(e, dir < 0);
+            e.flags = (e.flags & ~(1u << F_FACING)) | (dir < 0 ? 0u : (1u << F_FACING));
+        }
+        const int tk = ticker(e.flags);
+        if (tk > 0) {                                                                // impl:331-334
+            if (up_clear_m(e, L)) yd = -4;
+            e.flags = set_ticker(e.flags, tk - 1);
+        } else if (can_fall_m(e, L)) {                                               // impl:335-337
+            yd = 4;
+        }
+        e.px += xd;                                                                  // impl:339
+        if (yd > 0 && can_fall_m(e, L)) {                                            // impl:341-346, as in tick()
+            const int q = mod48(e.py);
+            if (q + yd <= 45) e.py += yd;
+            else do {
+                e.py++; yd--;
+                if (!can_fall_m(e, L)) yd = 0;
+            } while (yd > 0);
+        } else {
+            e.py += yd;                                                              // impl:348
+        }
+        bool near_x = false;
+#pragma unroll
+        for (int i = 0; i < NI; i++) near_x |= (i < L.n_items) && abs(e.px - (e.ix[i] + S / 2)) < 24;
+        if (near_x) pickups(e, L);
+        n++;
+        if (n >= TG_TICK_CAP) return false;
+    }
+    return true;
+}
+
+// The end of a drop / jump option once the player is aligned with its target column: NOP ticks until it cannot fall
+// (opts:233-238 / 299-304), the last of them on firm ground.  A NOP tick of a falling player (impl:335-348, no jump in
+// progress) moves it down one pixel at a time, at most 4, and stops at the first y where can_fall fails; playerx does
+// not change, so can_fall (impl:283-288: rows of y and y + 50 at x -+ 10 all OPEN) is a function of y alone: the
+// column profile `blk` (bit r = something at x -+ 10 in padded row r, closed doors included) gives the resting y
+// directly, and the fall takes ceil(distance / 4) ticks plus the final one.  No draws.  Returns false (nothing done)
+// when a jump is still rising or a key / coin is within reach of the column (pickups happen tick by tick).
+template <int NI>
+__device__ __forceinline__ bool fall_to_rest(Env<NI> &e, const LevelBlob &L, int &n) {
+    if (ticker(e.flags) != 0) return false;
+#pragma unroll
+    for (int i = 0; i < NI; i++) if (i < L.n_items && abs(e.px - (e.ix[i] + S / 2)) < 24) return false;
+    const int ca = pad_cell(e.px - 10), cb = pad_cell(e.px + 10);
+    uint32_t blk = L.col_nonopen[ca] | L.col_nonopen[cb];
+    const uint32_t closed = (e.flags >> F_DOORS) & 63u;
+    for (int d = 0; d < L.n_doors; d++) {
+        const int dc = L.door_cx[d] + PAD;
+        if (((closed >> d) & 1u) && (dc == ca || dc == cb)) blk |= 1u << (L.door_cy[d] + PAD);
+    }
+    // first y' >= y at which the row of y' or the row of y' + 50 holds something: the padded row r starts at pixel
+    // 48 * (r - PAD); the border rows are WALL, so both searches find a row
+    const int ra = pad_cell(e.py), rb = pad_cell(e.py + 50);
+    const uint32_t ma = blk >> ra, mb = blk >> rb;
+    const int ya = (ma & 1u) ? e.py : S * (ra + __ffs(ma) - 1 - PAD), yb = (mb & 1u) ? e.py : S * (rb + __ffs(mb) - 1 - PAD) - 50;
+    const int ystop = max(e.py, min(ya, yb));
+    const int ticks = (ystop - e.py + 3) / 4 + 1;
+    if (n + ticks > TG_TICK_CAP) return false;
+    e.py = ystop;
+    n += ticks; e.total_actions += ticks;
+    row_cache_drop(e);
+    return true;
+}
+
+// Runs option k (already known to be runnable, target column tcx from option_setup) to termination.  Returns the
+// number of primitive ticks; reward = -ticks - 4*[jump option] (impl:15-16,356-359).  `valid` = this lane has an env
+// and an option to run (every lane of a warp may call it).
+//
+// The two straight-line forms (walkers, ladders) are built from tight loops with branch-free bodies, which is what
+// the time of a step is made of (measured per 32-env chunk, tools/bench_chunks.py: a loop trip that picks one of
+// "four ticks / one tick / checked tick" cost a warp ~1000 cycles, 15 us per walker chunk):
+//   (1) fast-forward: eight (ladders: four) unchecked ticks per trip while every one of them is sure to start inside
+//       the safe stretch; the walkers compute two Philox blocks side by side;
+//   (2) the rest of the stretch from the cached block, branch-free: the moves are positive, so "tick k starts inside
+//       the stretch" is a comparison of the prefix sums with the distance left (consume_block);
+//   (3) the tick around an event (target reached, side blocked, item in range, a probed row changes), checked.
+template <bool TAPE, int NI, bool INTERACT_OK = true>
+__device__ __forceinline__ int run_option_to_end(Env<NI> &e, const LevelBlob &L, int k, int tcx, bool valid = true) {
     const int tpx = tcx * S + S / 2;
     const int s = (k == TG_GO_LEFT || k == TG_DOWN_LEFT || k == TG_JUMP_LEFT) ? -1 : 1;
     int n = 0;
-    bool done = false;
-    if (k <= TG_GO_RIGHT) {
-        // Straight-line form of the go_left / go_right tick for the common situation: no jump in progress
-        // and ground under the feet.  Then tick(LEFT/RIGHT) (impl:290-359) reduces to: count the action, move
-        // by noisy() if the side probe is free (and face that way), pick up.  playery never changes, so the
-        // two row masks are loop constants.  Any other situation (ticker > 0, can_fall) leaves the loop
-        // *before* the tick is executed and the general loop below takes over from the same state.
+    bool done = false;           // the option has terminated
+    // ---- go_left / go_right: straight-line form of the tick for the common situation: no jump in progress and ground
+    // under the feet.  Then tick(LEFT/RIGHT) (impl:290-359) reduces to: count the action, move by noisy() if the side
+    // probe is free (and face that way), pick up.  playery never changes, so the two row masks are loop constants.  Any
+    // other situation (ticker > 0, can_fall) leaves the loop *before* the tick and the general loop below takes over.
+    // Inside [px .. bound] (walk_safe_bound) a tick is just "count, move by noisy()": no probe can change, the target is
+    // not reached, nothing can be picked up.
+    // The drop options walk the same way until the ground ends or the target column is reached (opts:231-244 /
+    // 426-439 return LEFT / RIGHT until aligned): they take the unchecked part of the loop and leave before (3).
+    const bool drop = k == TG_DOWN_LEFT || k == TG_DOWN_RIGHT;
+    if (valid && (k <= TG_GO_RIGHT || drop)) {
         if (e.m_py != fall_key(e.py)) fall_cache_fill(e, L, fall_key(e.py));
         if (e.m_py_side != side_key(e.py)) side_cache_fill(e, L, side_key(e.py));
         const uint32_t mside = e.m_side, mfall = e.m_fall;
-        // Inside [px .. bound] (walk_safe_bound) a tick is just "count, move by noisy()": no probe can change,
-        // the target is not reached, nothing can be picked up.  Such ticks run without any check as long as the
-        // largest move (4 px) cannot leave the interval; the ticks around an event take the checked form below.
+        const bool neg = s < 0;
         int bound = ticker(e.flags) == 0 ? walk_safe_bound(e, L, s, tpx, mside, mfall) : e.px - s;
         for (;;) {
-            if (s * (bound - e.px) >= 4) {
-                if (!TAPE) {
-                    // one Philox block = four ticks
-                    while (s * (bound - e.px) >= 16 && ((e.draws - e.d0) & 3u) == 0u && n <= TG_TICK_CAP - 4) {
-                        uint32_t a, b, c, d;
-                        philox4x32_10(e.d0, (e.draws - e.d0) >> 2, e.id_lo, e.id_hi, e.key0, e.key1, a, b, c, d);
-                        e.draws += 4; n += 4;
-                        e.px += (s < 0 ? -16 : 8) + noisy_r_from_w(a) + noisy_r_from_w(b) + noisy_r_from_w(c) + noisy_r_from_w(d);
-                    }
+            const int n0 = n;
+            if (!TAPE) {
+                // (1) the largest move is 4 px: eight ticks all start inside the stretch when 28 px further on one still does
+                while (s * (bound - e.px) >= 32 && ((e.draws - e.d0) & 3u) == 0u && n <= TG_TICK_CAP - 8) {
+                    const uint32_t b = (e.draws - e.d0) >> 2;
+                    uint32_t x0, x1, x2, x3, y0, y1, y2, y3;
+                    philox4x32_10_x2(e.d0, b, e.id_lo, e.id_hi, e.key0, e.key1, x0, x1, x2, x3, y0, y1, y2, y3);
+                    const int sr = (noisy_r_from_w(x0) + noisy_r_from_w(x1)) + (noisy_r_from_w(x2) + noisy_r_from_w(x3)) +
+                                   (noisy_r_from_w(y0) + noisy_r_from_w(y1)) + (noisy_r_from_w(y2) + noisy_r_from_w(y3));
+                    e.px += (neg ? -32 : 16) + sr;                                 // eight moves of noisy(-4) / noisy(+4)
+                    e.draws += 8; n += 8;
                 }
-                while (s * (bound - e.px) >= 4 && n < TG_TICK_CAP) { e.px += noisy<TAPE>(e, s < 0); n++; }
-                e.flags = (e.flags & ~(1u << F_FACING)) | (s < 0 ? 0u : (1u << F_FACING));
-                if (n >= TG_TICK_CAP) { e.total_actions += n; e.flags |= 1u << F_ERROR; return n; }
+                // (2)
+                for (;;) {
+                    const int D = s * (bound - e.px) - 4;
+                    if (D < 0 || n > TG_TICK_CAP - 4) break;
+                    ensure_block(e);
+                    int moved;
+                    n += consume_block(e, neg, D, 4, moved);
+                    e.px += neg ? -moved : moved;
+                }
+            } else {
+                while (s * (bound - e.px) >= 4 && n < TG_TICK_CAP) { e.px += noisy<true>(e, neg); n++; }
             }
+            if (n != n0) e.flags = (e.flags & ~(1u << F_FACING)) | (neg ? 0u : (1u << F_FACING));
+            if (n >= TG_TICK_CAP) { e.flags |= 1u << F_ERROR; done = true; break; }
+            // (3)
+            if (drop) break;
             if (ticker(e.flags) != 0 ||
-                (((mfall >> pad_cell(e.px - 10)) | (mfall >> pad_cell(e.px + 10))) & 1u) == 0u) break;
+                (((mfall >> pad_cell(e.px - 10)) | (mfall >> pad_cell(e.px + 10))) & 1u) == 0u) break;   // jumping or falling: the general loop
             done = abs(tpx - e.px) < 4;                   // opts:80-85: the action of the final policy step still runs
             const int len0 = bag_len(e.flags);
             if (((mside >> pad_cell(e.px + 16 * s)) & 1u) == 0u) {
-                e.px += noisy<TAPE>(e, s < 0);
-                e.flags = (e.flags & ~(1u << F_FACING)) | (s < 0 ? 0u : (1u << F_FACING));
+                if (!TAPE) ensure_block(e);
+                e.px += noisy_cached<TAPE>(e, neg);
+                e.flags = (e.flags & ~(1u << F_FACING)) | (neg ? 0u : (1u << F_FACING));
             }
             pickups(e, L);
             n++;
             if (done) break;
-            if (n >= TG_TICK_CAP) { e.total_actions += n; e.flags |= 1u << F_ERROR; return n; }
+            if (n >= TG_TICK_CAP) { e.flags |= 1u << F_ERROR; done = true; break; }
             if (s * (e.px - bound) > 0 || bag_len(e.flags) != len0) bound = walk_safe_bound(e, L, s, tpx, mside, mfall);
         }
         e.total_actions += n;
-        if (done) return n;
-    } else if (k <= TG_DOWN_LADDER && ticker(e.flags) == 0) {
-        // Straight-line form of the up_ladder / down_ladder tick (opts:160-189 + impl:290-359).  playerx never changes,
-        // so the two probes of every tick look at fixed columns: a column profile per probe (bit r = the probe's
-        // cells of padded row r) turns them into register bit tests -- lad: LADDER at x -+ 12 (impl:240-257),
-        // blk: anything but OPEN at x -+ 10, closed doors included (impl:283-288; doors cannot move during the option).
-        // While the ladder probe holds and the player cannot fall, tick(UP/DOWN) is: count the action, move by noisy(),
-        // pick up.  Any other situation leaves the loop *before* the tick and the general loop below takes over from the
-        // same state (the terminating NOP tick included).  Building the profiles costs about two general ticks; ladder
-        // options last 17 ticks on average, and they are the long pole of small batches (4096 envs: 50.6 -> 39.8 us).
+    }
+    // ---- up_ladder / down_ladder (opts:160-189 + impl:290-359), straight-line form.  playerx never changes, so the
+    // two probes of every tick look at fixed columns: a column profile per probe (bit r = the probe's cells of padded
+    // row r) turns them into register bit tests -- lad: LADDER at x -+ 12 (impl:240-257), blk: anything but OPEN at
+    // x -+ 10, closed doors included (impl:283-288; doors cannot move during the option).  While the ladder probe holds
+    // and the player cannot fall, tick(UP/DOWN) is: count the action, move by noisy(), pick up.  The probes only change
+    // when one of the probed pixel rows (y-4, y, y+44, y+50 going up; y, y+50, y+51 going down) enters another cell row:
+    // `room` is the distance to the first such change, the stretch inside which ticks run unchecked.  A falling player
+    // leaves the loop *before* the tick and the general loop below takes over from the same state; the NOP tick that
+    // ends the option (opts:168-173 / 184-189) is taken here.
+    if (valid && (k == TG_UP_LADDER || k == TG_DOWN_LADDER) && ticker(e.flags) == 0) {
         const bool up = (k == TG_UP_LADDER);
         const int c0 = pad_cell(e.px - 12), c1 = pad_cell(e.px + 12), ca = pad_cell(e.px - 10), cb = pad_cell(e.px + 10);
-        uint32_t lad = 0, blk = 0;
-        const int nrows = L.ch + 2 * PAD;
-        for (int r = 0; r < nrows; r++) {
-            const uint32_t ml = L.row_ladder[r], mn = L.row_nonopen[r] | door_bits(L, e.flags, r);
-            lad |= (((ml >> c0) | (ml >> c1)) & 1u) << r;
-            blk |= (((mn >> ca) | (mn >> cb)) & 1u) << r;
+        const uint32_t lad = L.col_ladder[c0] | L.col_ladder[c1];
+        uint32_t blk = L.col_nonopen[ca] | L.col_nonopen[cb];
+        {
+            const uint32_t closed = (e.flags >> F_DOORS) & 63u;
+            for (int d = 0; d < L.n_doors; d++) {
+                const int dc = L.door_cx[d] + PAD;
+                if (((closed >> d) & 1u) && (dc == ca || dc == cb)) blk |= 1u << (L.door_cy[d] + PAD);
+            }
         }
         bool near_item = false;                     // an item in this column's pick-up range (impl:350-354)?  else no pickups at all
 #pragma unroll
@@ -648,55 +855,81 @@ __device__ __forceinline__ int run_option_to_end(Env<NI> &e, const LevelBlob &L,
             const int r1 = pad_cell(py);
             const uint32_t probe = up ? ((lad >> pad_cell(py - 4)) | (lad >> r1) | (lad >> pad_cell(py + 44)))
                                       : ((lad >> r1) | (lad >> min(r1 + 1, pad_cell(py + 51))) | (lad >> pad_cell(py + 51)));
-            if (!(probe & 1u) || (up && py <= 1)) break;                        // opts:168-173 / 184-189: the NOP tick follows
-            if ((((blk >> r1) | (blk >> pad_cell(py + 50))) & 1u) == 0u) break;   // can_fall: the general tick
-            e.py = py + noisy<TAPE>(e, up);
-            n++;
-            if (near_item) pickups(e, L);
-            if (n >= TG_TICK_CAP) { e.total_actions += n; e.flags |= 1u << F_ERROR; return n; }
+            if ((((blk >> r1) | (blk >> pad_cell(py + 50))) & 1u) == 0u) break;       // can_fall (also when the final NOP tick starts a fall): the general loop
+            if (!(probe & 1u) || (up && py <= 1)) {
+                n++;                                // the NOP tick on firm ground (impl:290-359): count, pick up
+                if (near_item) pickups(e, L);
+                done = true;
+                break;
+            }
+            int room = up ? min(min(min(mod48(py - 4), mod48(py)), min(mod48(py + 44), mod48(py + 50))), py - 2)
+                          : 47 - max(max(mod48(py), mod48(py + 50)), mod48(py + 51));
+            if (!TAPE && !near_item) {
+                // (1) four ticks all start inside the stretch when 12 px further on one still does
+                while (room >= 12 && ((e.draws - e.d0) & 3u) == 0u && n <= TG_TICK_CAP - 4) {
+                    const uint4 o = philox_block(e.d0, (e.draws - e.d0) >> 2, e.id_lo, e.id_hi, e.key0, e.key1);
+                    e.w0 = o.x; e.w1 = o.y; e.w2 = o.z; e.w3 = o.w;
+                    const int sr = (noisy_r_from_w(o.x) + noisy_r_from_w(o.y)) + (noisy_r_from_w(o.z) + noisy_r_from_w(o.w));
+                    const int mag = up ? 16 - sr : 8 + sr;                          // four moves of noisy(-4) / noisy(+4)
+                    e.py += up ? -mag : mag; room -= mag;
+                    e.draws += 4; n += 4;
+                }
+                // (2)
+                while (room >= 0 && n <= TG_TICK_CAP - 4) {
+                    ensure_block(e);
+                    int moved;
+                    n += consume_block(e, up, room, 4, moved);
+                    e.py += up ? -moved : moved; room -= moved;
+                }
+            }
+            while (room >= 0 && n < TG_TICK_CAP) {      // draw tape, an item within reach, or close to the tick cap: one tick at a time
+                const int dlt = noisy<TAPE>(e, up);
+                e.py += dlt; room -= abs(dlt);
+                n++;
+                if (near_item) pickups(e, L);
+            }
+            if (n >= TG_TICK_CAP) { e.flags |= 1u << F_ERROR; done = true; break; }
         }
         e.total_actions += n;
     }
-    do {
-        int act, lad = -1;
-        const bool al = abs(tpx - e.px) < 4;              // close_enough_*  (opts:69-72 ...)
-        if (k <= TG_GO_RIGHT) {                           // opts:74-85 / 146-157
-            done = al; act = (s < 0) ? A_LEFT : A_RIGHT;
-        } else if (k == TG_UP_LADDER) {                   // opts:168-173
-            done = !ladder_probe(L, e.px, e.py, true); act = done ? A_NOP : A_UP; lad = 1;
-        } else if (k == TG_DOWN_LADDER) {                 // opts:184-189
-            done = !ladder_probe(L, e.px, e.py, false); act = done ? A_NOP : A_DOWN; lad = 1;
-        } else if (k == TG_INTERACT) {                    // opts:457-460
-            done = true; act = A_INTERACT;
-        } else if (k <= TG_DOWN_RIGHT) {                  // opts:231-244 / 426-439
-            if (al) { done = !can_fall_m(e, L); act = A_NOP; }
-            else act = (s < 0) ? A_LEFT : A_RIGHT;
-        } else {                                          // opts:297-314 / 367-384
-            if (n == 0) act = A_JUMP;
-            else if (al) { done = !can_fall_m(e, L); act = A_NOP; }
-            else {
-                bool blocked = !side_free_m(e, L, e.px + 16 * s);
-                bool grounded = !can_fall_m(e, L);
-                bool rev = grounded && blocked;
-                act = ((s < 0) != rev) ? A_LEFT : A_RIGHT;
-            }
-        }
-        tick<TAPE>(e, L, act, lad);
-        n++;
-        if (n >= TG_TICK_CAP && !done) { e.flags |= 1u << F_ERROR; break; }
-    } while (!done);
-    return n;
-}
-
-// Setup + run (0 ticks = not runnable: the reference returns None, opt:22-23).
-template <bool TAPE, int NI>
-__device__ __forceinline__ int run_option(Env<NI> &e, const LevelBlob &L, int k) {
-    int tcx; bool err;
-    if (!option_setup(e, L, k, tcx, err)) {
-        if (err) e.flags |= 1u << F_ERROR;
-        return 0;
+    // ---- drops and jumps: the JUMP tick (opts:297-300), then LEFT / RIGHT ticks until aligned; the fall at the end is
+    // taken in closed form by the loop below (fall_to_rest)
+    if (valid && !done && k >= TG_DOWN_LEFT) {
+        if (k >= TG_JUMP_LEFT && n == 0) { tick<TAPE, NI, false>(e, L, A_JUMP); n++; }
+        if (!move_until_aligned<TAPE>(e, L, k >= TG_JUMP_LEFT, s, tpx, n)) { e.flags |= 1u << F_ERROR; done = true; }
     }
-    return run_option_to_end<TAPE>(e, L, k, tcx);
+    // ---- everything else, and what the loops above left: policy step + general tick, one lane at its own pace ----
+    if (valid && !done) {
+        do {
+            int act, lad = -1;
+            const bool al = abs(tpx - e.px) < 4;              // close_enough_*  (opts:69-72 ...)
+            if (k <= TG_GO_RIGHT) {                           // opts:74-85 / 146-157
+                done = al; act = (s < 0) ? A_LEFT : A_RIGHT;
+            } else if (k == TG_UP_LADDER) {                   // opts:168-173
+                done = !ladder_probe(L, e.px, e.py, true); act = done ? A_NOP : A_UP; lad = 1;
+            } else if (k == TG_DOWN_LADDER) {                 // opts:184-189
+                done = !ladder_probe(L, e.px, e.py, false); act = done ? A_NOP : A_DOWN; lad = 1;
+            } else if (k == TG_INTERACT) {                    // opts:457-460
+                done = true; act = A_INTERACT;
+            } else if (k <= TG_DOWN_RIGHT) {                  // opts:231-244 / 426-439
+                if (al) { if (fall_to_rest(e, L, n)) { done = true; break; } done = !can_fall_m(e, L); act = A_NOP; }
+                else act = (s < 0) ? A_LEFT : A_RIGHT;
+            } else {                                          // opts:297-314 / 367-384
+                if (n == 0) act = A_JUMP;
+                else if (al) { if (fall_to_rest(e, L, n)) { done = true; break; } done = !can_fall_m(e, L); act = A_NOP; }
+                else {
+                    bool blocked = !side_free_m(e, L, e.px + 16 * s);
+                    bool grounded = !can_fall_m(e, L);
+                    bool rev = grounded && blocked;
+                    act = ((s < 0) != rev) ? A_LEFT : A_RIGHT;
+                }
+            }
+            tick<TAPE, NI, INTERACT_OK>(e, L, act, lad);
+            n++;
+            if (n >= TG_TICK_CAP && !done) { e.flags |= 1u << F_ERROR; break; }
+        } while (!done);
+    }
+    return n;
 }
 
 // Rough number of primitive ticks option k will take from this state (only used to group
@@ -729,14 +962,114 @@ __device__ __forceinline__ int estimate_ticks(const Env<NI> &e, const LevelBlob 
 }
 
 template <int NI>
-__device__ __forceinline__ uint32_t available_bits(const Env<NI> &e, const LevelBlob &L) {   // tg:83-89
-    uint32_t m = 0;
-    for (int k = 0; k < TG_NUM_OPTIONS; k++) {
-        int tcx; bool err;
-        if (option_setup(e, L, k, tcx, err)) m |= 1u << k;
-    }
-    return m;
+__device__ __forceinline__ bool is_done(const Env<NI> &e, const LevelBlob &L) {    // tg:95
+    return has_gold(L, e.flags) && floordiv48(e.py + S / 2) == 0;
 }
+
+// The plan word of an env (tg_types.h PL_*): can_run of the nine options (tg:83-89), the done predicate (tg:95),
+// "the reference would raise" for the two drop options, and a length class per option for the step kernel's sort.
+// A function of (position, flags, item positions) only; every kernel that stores an env's state stores its plan.
+// All nine can_run predicates are evaluated together on the row masks of the player's cell row and its two
+// neighbours (the same formulation as walk_setup / ladder_probe; option_setup keeps the per-option form the
+// option lanes use, and the parity tests compare both with the oracle's masks).  Out of line, scalar arguments.
+__device__ __forceinline__ uint32_t plan_len(int ticks) { return (uint32_t)min(ticks / 10, 11); }
+template <int NI>
+__device__ __noinline__ uint64_t compute_plan(const LevelBlob *Lp, uint32_t pxy, uint32_t flags, uint32_t it0, uint32_t it1,
+                                              uint32_t it2, uint32_t it3) {
+    const LevelBlob &L = *Lp;
+    const int px = (int)(pxy & 0xFFFu), py = (int)(int16_t)(pxy >> 16);
+    const int cxp = pad_cell(px), r = pad_cell(py + S / 2);                       // padded player cell (impl:441-445)
+    const uint32_t closed = (flags >> F_DOORS) & 63u;
+    auto doors = [&](int row) -> uint32_t { const int li = L.row_lut[row]; return li ? L.door_lut[li - 1][closed] : 0u; };
+    const uint32_t D0 = doors(r), D1 = doors(r + 1);
+    const uint32_t open_m = ~(L.row_nonopen[r - 1] | doors(r - 1)), open_0 = ~(L.row_nonopen[r] | D0), open_1 = ~(L.row_nonopen[r + 1] | D1);
+    const uint32_t wall_0 = L.row_solid[r];                                        // WALL proper (a closed door reads DOOR)
+    uint32_t lo = 0, len_lo = 0, len_hi = 0;                                      // len: 9 x 4 bits = 32 + 4
+    const uint32_t items[4] = {it0, it1, it2, it3};
+
+    // go_left / go_right (opts:23-67, :95-139), as walk_setup
+    {
+        uint32_t obj = L.row_static_obj[r] | D0;                                   // impl:402-409
+#pragma unroll
+        for (int i = 0; i < NI; i++) {
+            const int icx = (int)(int16_t)(items[i] & 0xFFFFu) / S + PAD, icy = (int)(int16_t)(items[i] >> 16) / S + PAD;
+            if (i < L.n_items && icy == r && icx >= 0 && icx < TSTRIDE) obj |= 1u << icx;
+        }
+        const uint32_t nb = wall_0 | D0 | open_1;
+        const uint32_t tm = L.row_ladder[r - 1] | L.row_ladder[r + 1] | obj;
+        const uint32_t okm = open_0 & ~open_1;                                     // opts:34-39
+        const uint32_t candL = (tm | (nb << 1)) & ((1u << cxp) - 1u) & ~((1u << PAD) - 1u);
+        if (candL) {
+            const int txp = 31 - __clz(candL);
+            const uint32_t range = ((2u << cxp) - 1u) & ~((1u << txp) - 1u);
+            if ((okm & range) == range) { lo |= 1u << TG_GO_LEFT; len_lo |= plan_len((abs((txp - PAD) * S + S / 2 - px) + 2) / 3 + 1) << (4 * TG_GO_LEFT); }
+        }
+        const uint32_t candR = (tm | (nb >> 1)) & ~((2u << cxp) - 1u);
+        if (candR) {
+            const int txp = __ffs(candR) - 1;
+            const uint32_t range = ((2u << txp) - 1u) & ~((1u << cxp) - 1u);
+            if ((okm & range) == range) { lo |= 1u << TG_GO_RIGHT; len_lo |= plan_len((abs((txp - PAD) * S + S / 2 - px) + 2) / 3 + 1) << (4 * TG_GO_RIGHT); }
+        }
+    }
+    // up_ladder / down_ladder (opts:165-166, :181-182 = impl:240-257)
+    if (ladder_probe(L, px, py, true)) {
+        int rr = r;
+        while (rr > 0 && (((L.row_ladder[rr] | L.row_ladder[rr - 1]) >> cxp) & 1u)) rr--;
+        lo |= 1u << TG_UP_LADDER; len_lo |= plan_len(max(2, (py - (rr - PAD) * S) / 3)) << (4 * TG_UP_LADDER);
+    }
+    if (ladder_probe(L, px, py, false)) {
+        int rr = r + 1;
+        while (rr < TSTRIDE - 1 && ((L.row_ladder[rr] >> cxp) & 1u)) rr++;
+        lo |= 1u << TG_DOWN_LADDER; len_lo |= plan_len(max(2, ((rr - PAD) * S - py - S) / 3 + 2)) << (4 * TG_DOWN_LADDER);
+    }
+    // interact (opts:446-455): one tick
+    {
+        bool ok = false;
+        for (int i = 0; i < L.n_handles; i++) ok |= near_px(px, py, L.handle_cx[i] * S, L.handle_cy[i] * S, 36 * 36);
+        if (has_key(L, flags))
+            for (int i = 0; i < L.n_bolts; i++) ok |= near_px(px, py, L.bolt_cx[i] * S, L.bolt_cy[i] * S, 24 * 24);
+        if (ok) lo |= 1u << TG_INTERACT;
+    }
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int s = side ? 1 : -1, c1 = cxp + s, c2 = cxp + 2 * s;
+        // down_left / down_right (opts:199-221, :394-416): the side cell and the one below it are OPEN; the target row is
+        // the first cell that is not, and the reference raises when there is none
+        if ((open_0 >> c1) & (open_1 >> c1) & 1u) {
+            int rr = r + 1;
+            bool err = false;
+            for (;;) {
+                if (((L.row_nonopen[rr] | doors(rr)) >> c1) & 1u) break;
+                rr++;
+                if (rr - PAD >= L.ch) { err = true; break; }
+            }
+            const int k = side ? TG_DOWN_RIGHT : TG_DOWN_LEFT;
+            if (err) lo |= 1u << (side ? PL_ERR_DR : PL_ERR_DL);
+            else { lo |= 1u << k; len_lo |= plan_len((abs((c1 - PAD) * S + S / 2 - px) + 2) / 3 + 12 * (rr - r - 1) + 2) << (4 * k); }
+        }
+        // jump_left / jump_right (opts:254-287, :324-357): OPEN above and diagonally above, and a landing (OPEN over WALL)
+        // one or two columns away in the row above
+        if ((open_m >> cxp) & (open_m >> c1) & 1u) {
+            int tc = 0;
+            if ((wall_0 >> c1) & 1u) tc = c1;
+            else if ((open_m >> c2) & (wall_0 >> c2) & 1u) tc = c2;
+            if (tc) {
+                const uint32_t lc = plan_len(24 + (abs((tc - PAD) * S + S / 2 - px) + 2) / 3);
+                if (side) { lo |= 1u << TG_JUMP_RIGHT; len_hi |= lc; } else { lo |= 1u << TG_JUMP_LEFT; len_lo |= lc << (4 * TG_JUMP_LEFT); }
+            }
+        }
+    }
+    if (has_gold(L, flags) && r == PAD) lo |= 1u << PL_TERM;                       // tg:95
+    return (uint64_t)lo | ((uint64_t)len_lo << PL_LEN) | ((uint64_t)len_hi << (PL_LEN + 32));
+}
+template <int NI>
+__device__ __forceinline__ uint64_t plan_of(const Env<NI> &e, const LevelBlob &L) {
+    return compute_plan<NI>(&L, pack_player(e.px, e.py, 0u), e.flags, pack_xy(e.ix[0], e.iy[0]),
+                            NI > 1 ? pack_xy(e.ix[NI > 1 ? 1 : 0], e.iy[NI > 1 ? 1 : 0]) : 0u,
+                            NI > 2 ? pack_xy(e.ix[NI > 2 ? 2 : 0], e.iy[NI > 2 ? 2 : 0]) : 0u,
+                            NI > 3 ? pack_xy(e.ix[NI > 3 ? 3 : 0], e.iy[NI > 3 ? 3 : 0]) : 0u);
+}
+__device__ __forceinline__ int plan_len_class(uint64_t p, int k) { return (int)((p >> (PL_LEN + 4 * k)) & 15u); }
 
 // ---------------------------------------------------------------------------
 // reset  (impl:55-73, impl:168-178, objs:106-115) -- draws: one per handle (file order), then a gauss pair
@@ -778,21 +1111,22 @@ __device__ __forceinline__ float obs_quot(const float *__restrict__ lut, int v, 
     const unsigned idx = (unsigned)(v + S);
     return idx < (unsigned)OBS_LUT_N ? __ldg(lut + idx) : __fdiv_rn((float)v, (float)extent);
 }
-// pre0, pre1 (npre of them valid) = angles of the first handles already in registers (requested together with the state).
+// Writes the row to `o` and, when given, to `o2` (the sparse record of tg_step_host_sparse): every value is computed once.
 template <int NI>
 __device__ __forceinline__ void write_obs(const Env<NI> &e, const LevelBlob &L, const float *__restrict__ lut,
-                                          float *__restrict__ o, int obs_dim, int npre = 0, double pre0 = 0.0, double pre1 = 0.0) {
+                                          float *__restrict__ o, int obs_dim, float *__restrict__ o2 = nullptr) {
     const int W = L.cw * S, H = L.ch * S;
     const int nk = L.obs_dim;
+    auto put = [&](int k, float v) { if (o) o[k] = v; if (o2) o2[k] = v; };
     if (L.obs_prog[31] == 1) {       // the shipped layout's slot order (two handles, key, bolt, gold): straight-line code
         const float *lx = lut, *ly = lut + OBS_LUT_N;
-        const double a0 = (npre > 0) ? pre0 : e.angles[0], a1 = (npre > 1) ? pre1 : e.angles[e.n];
-        o[0] = obs_quot(lx, e.px, W); o[1] = obs_quot(ly, e.py, H);
-        o[2] = (float)a0; o[3] = (float)a1;
-        o[4] = obs_quot(lx, e.ix[0], W); o[5] = obs_quot(ly, e.iy[0], H);
-        o[6] = ((e.flags >> F_BOLTS) & 1u) ? 1.0f : 0.0f;
-        o[7] = obs_quot(lx, e.ix[NI > 1 ? 1 : 0], W); o[8] = obs_quot(ly, e.iy[NI > 1 ? 1 : 0], H);
-        for (int k = 9; k < obs_dim; k++) o[k] = 0.0f;
+        const double a0 = e.angles[0], a1 = e.angles[e.n];
+        put(0, obs_quot(lx, e.px, W)); put(1, obs_quot(ly, e.py, H));
+        put(2, (float)a0); put(3, (float)a1);
+        put(4, obs_quot(lx, e.ix[0], W)); put(5, obs_quot(ly, e.iy[0], H));
+        put(6, ((e.flags >> F_BOLTS) & 1u) ? 1.0f : 0.0f);
+        put(7, obs_quot(lx, e.ix[NI > 1 ? 1 : 0], W)); put(8, obs_quot(ly, e.iy[NI > 1 ? 1 : 0], H));
+        for (int k = 9; k < obs_dim; k++) put(k, 0.0f);
         return;
     }
     for (int k = 0; k < nk; k++) {
@@ -803,17 +1137,12 @@ __device__ __forceinline__ void write_obs(const Env<NI> &e, const LevelBlob &L, 
 #pragma unroll
             for (int q = 0; q < NI; q++) if (q == i) { x = e.ix[q]; y = e.iy[q]; }
             v = (op == OP_IX) ? obs_quot(lut, x, W) : obs_quot(lut + OBS_LUT_N, y, H);
-        } else if (op == OP_ANGLE) v = (float)((i < npre) ? (i == 0 ? pre0 : pre1) : e.angles[(int64_t)i * e.n]);
+        } else if (op == OP_ANGLE) v = (float)e.angles[(int64_t)i * e.n];
         else if (op == OP_BOLT) v = ((e.flags >> (F_BOLTS + i)) & 1u) ? 1.0f : 0.0f;
         else v = (op == OP_PX) ? obs_quot(lut, e.px, W) : obs_quot(lut + OBS_LUT_N, e.py, H);
-        o[k] = v;
+        put(k, v);
     }
-    for (int k = nk; k < obs_dim; k++) o[k] = 0.0f;
-}
-
-template <int NI>
-__device__ __forceinline__ bool is_done(const Env<NI> &e, const LevelBlob &L) {    // tg:95
-    return has_gold(L, e.flags) && floordiv48(e.py + S / 2) == 0;
+    for (int k = nk; k < obs_dim; k++) put(k, 0.0f);
 }
 
 // ---------------------------------------------------------------------------
@@ -868,16 +1197,6 @@ __device__ void init_with_state_env(Env<NI> &e, const LevelBlob &L, const double
 // ---------------------------------------------------------------------------
 // packed state <-> registers
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pack_xy(int x, int y) { return ((uint32_t)x & 0xFFFFu) | ((uint32_t)y << 16); }
-// core.x = playerx (12 bits, 0 <= x < 26*48) | sticky handle flags (4 bits) | playery << 16
-__device__ __forceinline__ uint32_t pack_player(int px, int py, uint32_t sticky) {
-    return ((uint32_t)px & 0xFFFu) | ((sticky & 15u) << 12) | ((uint32_t)py << 16);
-}
-__device__ __forceinline__ int core_px(uint32_t v) { return (int)(v & 0xFFFu); }
-__device__ __forceinline__ uint32_t core_sticky(uint32_t v) { return (v >> 12) & 15u; }
-__device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xFFFFu); }
-__device__ __forceinline__ int hi16(uint32_t v) { return (int)(int16_t)(v >> 16); }
-
 // position / flags / items only (enough for can_run and the option targets)
 template <int NI>
 __device__ __forceinline__ void load_core(Env<NI> &e, const BatchView &B, int64_t i, uint4 c) {
@@ -913,6 +1232,7 @@ __device__ __forceinline__ void load_env(Env<NI> &e, const BatchView &B, int64_t
     uint64_t id = (uint64_t)(B.first_env_id + i);
     e.id_lo = (uint32_t)id; e.id_hi = (uint32_t)(id >> 32);
     e.tape = B.tape ? B.tape + B.tape_off[i] : nullptr;
+    e.tape_len = B.tape ? (uint32_t)(B.tape_off[i + 1] - B.tape_off[i]) : 0u;
     e.angles = B.angles + i; e.n = B.n;
 }
 

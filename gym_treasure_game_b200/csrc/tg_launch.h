@@ -5,6 +5,25 @@
 
 namespace tg {
 
+// Function attributes (dynamic shared memory opt-in) and SM counts are per device, and one process may hold envs on
+// several devices: everything the launchers cache is indexed by the current device ordinal.
+constexpr int MAX_DEVICES = 64;
+inline int device_slot() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEVICES) d = 0;
+    return d;
+}
+inline int device_sm_count() {
+    static int sms[MAX_DEVICES] = {};
+    const int d = device_slot();
+    if (!sms[d]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v < 1) { cudaGetLastError(); v = 148; }
+        sms[d] = v;
+    }
+    return sms[d];
+}
+
 // render assets of one level on the device
 struct RenderAssets {
     const uint8_t *background;   // [frame_h][frame_w][3]
@@ -17,11 +36,13 @@ struct RenderView {
     unsigned long long *job_counter;   // device word used by the streaming renderer to hand out jobs
 };
 
-cudaError_t launch_step(const BatchView &B, int ni, const int32_t *actions, float *obs, float *reward,
+cudaError_t launch_step(const BatchView &B, int ni, int forced_tile, const int32_t *actions, float *obs, float *reward,
                         uint8_t *done, uint8_t *ran, uint16_t *avail, cudaStream_t s);
 cudaError_t launch_reset(const BatchView &B, int ni, const uint8_t *mask, float *obs, cudaStream_t s);
 cudaError_t launch_primitive(const BatchView &B, int ni, const int32_t *actions, float *obs, float *reward, uint8_t *done, cudaStream_t s);
 cudaError_t launch_init_with_state(const BatchView &B, int ni, const double *states, const uint8_t *mask, cudaStream_t s);
+// observation rows of the envs [r_begin, r_begin + r_count) from their stored state
+cudaError_t launch_obs(const BatchView &B, int ni, float *obs, cudaStream_t s);
 cudaError_t launch_mask(const BatchView &B, int ni, uint8_t *mask, cudaStream_t s);
 cudaError_t launch_get_state(const BatchView &B, const tg_state_view &v, cudaStream_t s);
 cudaError_t launch_set_state(const BatchView &B, const tg_state_view &v, cudaStream_t s);
@@ -31,6 +52,5 @@ cudaError_t launch_blend(const BatchView &B, const RenderView &R, int64_t first,
                          uint8_t *surfaces, int alpha_objs, int alpha_player, cudaStream_t s);
 cudaError_t launch_blit_alpha(uint8_t *target, int tw, int th, const uint8_t *source, int sw, int sh, int channels,
                               int x0, int y0, int opacity, cudaStream_t s);
-cudaError_t render_configure();   // one-time function attributes (dynamic shared memory opt-in)
 
 }  // namespace tg

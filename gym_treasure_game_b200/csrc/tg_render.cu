@@ -619,20 +619,15 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int E
     if (tid == 0) wait_bulk_read(0);
 }
 
-static bool g_render_configured = false;
-static int g_num_sms = 0;
-
-cudaError_t render_configure() {
-    if (g_render_configured) return cudaSuccess;
+// dynamic shared memory opt-in, once per device (function attributes are per device)
+static cudaError_t render_configure() {
+    static bool configured[MAX_DEVICES] = {};
+    const int d = device_slot();
+    if (configured[d]) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(tg_render_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tg_render_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    if (e != cudaSuccess) return e;
-    int dev = 0;
-    e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) g_render_configured = true;
+    if (e == cudaSuccess) configured[d] = true;
     return e;
 }
 
@@ -666,7 +661,7 @@ cudaError_t launch_render(const BatchView &B, const RenderView &R, int64_t first
         // resident CTA so that the dynamic job queue still balances (4096 frames: 256 -> 4.3, 64 -> 5.45 TB/s)
         static int eb_forced = -1;
         if (eb_forced < 0) { const char *v = getenv("TG_RENDER_EB"); eb_forced = v ? atoi(v) : 0; }
-        const int64_t slots = (int64_t)g_num_sms * per_sm;
+        const int64_t slots = (int64_t)device_sm_count() * per_sm;
         int eb = RS_EB_MAX;
         while (eb > 16 && (int64_t)(R.frame_h / ur) * ((count + eb - 1) / eb) < 8 * slots) eb >>= 1;
         if (eb_forced >= 16 && eb_forced <= RS_EB_MAX) eb = eb_forced;

@@ -51,34 +51,28 @@ constexpr int STEP_THREADS = TG_STEP_THREADS;
 constexpr int AUX_THREADS = 128;       // reset / mask kernels
 constexpr int NBUCKET = 64;          // length classes for the in-tile sort (bucket 0 = longest, 63 = not runnable)
 
-// debug instrumentation (tg_debug_phase_buffer): thread 0 of every CTA stamps the phase boundaries
-__device__ __forceinline__ void phase_stamp(const BatchView &B, int slot) {
+// debug instrumentation (tg_debug_phase_buffer): thread 0 of every CTA stamps the phase boundaries.  The timer read
+// is made to depend on a shared-memory load: BAR.SYNC.DEFER_BLOCKING lets a warp run ahead of the barrier until its next
+// memory access, so a bare special-register read right after __syncthreads() is taken before the barrier completes.
+__device__ __forceinline__ void phase_stamp(const BatchView &B, int slot, const volatile int *sh) {
     if (B.phase_ts && threadIdx.x == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        unsigned long long t = 0;
+        if (*sh != -0x7fffffff) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
         B.phase_ts[(size_t)blockIdx.x * 8 + slot] = t;
     }
 }
 
-// info word per env of the tile: bit 0 runnable, bit 1 reference-would-raise, bits 2-7 target column + 8,
-// bits 8-13 bucket, bits 14-17 option id (9 = not an option id), bit 18 runnable (kept by the later format)
-__device__ __forceinline__ uint32_t pack_info(bool ran, bool err, int tcx, int bucket, int a) {
-    return (ran ? 1u | (1u << 18) : 0u) | (err ? 2u : 0u) | ((uint32_t)((tcx + 8) & 63) << 2) | ((uint32_t)bucket << 8) | ((uint32_t)a << 14);
-}
-
-// Reset of an env whose option did not run (time limit): out of line and through memory, so that the common
-// path of phase 4 carries neither the RNG state nor the Box-Muller code.  The caller has stored acct.
-// `drawn` = uniforms the env has already consumed in this call (its option ran): the Philox blocks of a call are
-// numbered from the call's first draw (draw_w), so the reset continues that numbering.
-template <bool TAPE, int NI>
-__device__ __noinline__ void reset_in_memory(const BatchView &B, const LevelBlob *L, int64_t i, uint32_t drawn) {
-    Env<NI> e;
-    uint4 acct;
-    load_env(e, B, i, acct);
-    e.d0 = e.draws - drawn;
-    if (!TAPE && (drawn & 3u)) philox4x32_10(e.d0, drawn >> 2, e.id_lo, e.id_hi, e.key0, e.key1, e.w0, e.w1, e.w2, e.w3);
-    reset_env<TAPE>(e, *L);
-    store_env(e, B, i, acct);
+// The last CTA of a launch to finish (every CTA has read step_counter[0] by then) advances the batch's gym-step
+// counter when the launch is the last one of its API call, and re-arms the ticket.
+__device__ __forceinline__ void finish_launch(const BatchView &B) {
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned total = gridDim.x * gridDim.y;
+        if (atomicAdd(&B.step_counter[1], 1u) == total - 1u) {
+            B.step_counter[1] = 0u;
+            if (B.advance) B.step_counter[0] += 1u;
+        }
+    }
 }
 
 // exclusive scan of hist[0 .. 63] by warp 0 (two entries per lane)
@@ -91,287 +85,365 @@ __device__ __forceinline__ void scan64(int *hist, int lane) {
     hist[2 * lane] = excl; hist[2 * lane + 1] = excl + v0;
 }
 
+// The interact option (opts:442-460: one INTERACT tick, impl:321-329) through memory and out of line: lever flip,
+// trigger graph, handle angles and the key drop are rare (2.6 % of the steps under random actions) and large; kept out
+// of the option lanes' instruction stream.  Returns the uniforms drawn.
+template <bool TAPE, int NI>
+__device__ __noinline__ uint32_t interact_option_mem(const BatchView &B, const LevelBlob *Lp, int64_t i) {
+    Env<NI> e;
+    uint4 acct;
+    load_env(e, B, i, acct);
+    tick<TAPE, NI, true>(e, *Lp, A_INTERACT);
+    store_env(e, B, i, acct);
+    return e.draws - e.d0;
+}
+
+// acct.z of an env that ran and whose episode ended, between its option lane and the reset pass:
+// uniforms drawn in this call (16 bits) | primitive ticks (13) | jump option (1) | done bits (2)
+__device__ __forceinline__ uint32_t pack_pending(uint32_t drawn, int n, bool jump, uint32_t d) {
+    return min(drawn, 0xFFFFu) | ((uint32_t)n << 16) | ((jump ? 1u : 0u) << 29) | (d << 30);
+}
+
 // ---------------------------------------------------------------------------
-// tg_step_kernel: one CTA owns a tile of `tile` (<= TILE) consecutive environments.
-//   phase 0  counting sort of the tile by option id -> perm0[]: the classification below is a 9-way switch
-//            on the option, and with i.i.d. actions a warp in index order runs every case with 3-4 lanes
-//            (measured: can_run + length estimate were 30 % of the kernel's warp instructions at 2-6 active lanes)
-//   phase 1  in option order: evaluate can_run of the chosen option (+ target column), estimate its
-//            length in ticks; histogram the (code path, length) classes
-//   phase 2  counting sort of the runnable envs by class -> perm[]; their 32-env chunks ordered longest first
-//   phase 3  warps pull chunks from a shared counter: first the runnable chunks (a lane runs its env's option to
-//            termination and puts the state back), then every index-order chunk for the envs whose option did not
-//            run: time-limit / auto-reset / outputs with contiguous loads and full-line stores
-//   phase 5  (after a barrier) the envs that ran: reward / done / time-limit / auto-reset / outputs
-// Sorting puts the ~10-20 % runnable envs of a tile into a few full warps of similar length
-// instead of leaving 1-2 busy lanes in every warp (measured SIMT efficiency before: 2/32 lanes).
-// Results do not depend on the order: every env owns its RNG stream and state.
+// tg_step_kernel: one CTA owns a tile of `tile` consecutive environments (shared arrays sized for `cap` >= tile).
+//   phase A  index order, vector loads / stores: action + plan word + episode start of every env.  An env whose
+//            option cannot run (80 % under random actions; the reference returns None and leaves the state untouched,
+//            opt:22-23) is finished here: reward 0, ran 0, done (terminated from the plan, truncated from the episode
+//            start) -- 16 bytes read and 6 written, its state record is never loaded and its observation row is
+//            not rewritten (see tg_step in treasure_b200.h: rows only change when the env's state does).  A runnable
+//            env gets its sort bucket (code-path class major, length class from the plan minor) and its rank in the
+//            bucket (one shared-memory atomic).  Idle envs whose episode ended go on the reset list.
+//   sort     exclusive scan of the 64 bucket counts, scatter by rank -> perm[]; 32-env chunks ordered longest first
+//   phase B  warps pull chunks from a shared counter: a lane loads its env, runs the option to termination
+//            (run_option_to_end = opt:20-36 + impl:290-359) and finishes the gym step in place: reward, done
+//            (tg:95), time limit, new plan, state, observation row, outputs; an env whose episode ended goes on
+//            the reset list instead.
+//   phase C  (after a barrier) the reset list, full warps: reset_game (impl:55-73), plan, state, observation row.
+// Sorting puts the ~20 % runnable envs of a tile into full warps that run the same code path for a similar number
+// of ticks (one thread per env in index order: 2 of 32 lanes active, profiles/r01_step_v1_ncu.txt).  Results do not
+// depend on the order: every env owns its RNG stream and state.
 // ---------------------------------------------------------------------------
 #ifndef TG_STEP_MIN_BLOCKS
-#define TG_STEP_MIN_BLOCKS 3      // 80 registers, no spills, 3 CTAs per SM with 2364-env tiles: 9.9 G env-steps/s; 64 registers x 4 CTAs with
-                                  // 1772-env tiles spilled 132 bytes: 9.2 G (round 1, v10 kernel; the v4 kernel had preferred 64 registers)
+#define TG_STEP_MIN_BLOCKS 3
 #endif
-template <bool TAPE, int NI, int TILE>
+template <bool TAPE, int NI>
 __global__ void __launch_bounds__(STEP_THREADS, TG_STEP_MIN_BLOCKS)
-tg_step_kernel(const __grid_constant__ BatchView B, int tile, const int32_t *__restrict__ actions, float *__restrict__ obs,
+tg_step_kernel(const __grid_constant__ BatchView B, int tile, int cap, const int32_t *__restrict__ actions, float *__restrict__ obs,
                float *__restrict__ reward, uint8_t *__restrict__ done_out, uint8_t *__restrict__ ran_out,
                uint16_t *__restrict__ avail_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LevelBlob *levels = reinterpret_cast<LevelBlob *>(smem_raw);
+    uint8_t *code = smem_raw + (((size_t)B.n_levels * sizeof(LevelBlob) + 15) & ~(size_t)15);   // [cap] sort bucket, 255 = idle
+    uint16_t *rank = reinterpret_cast<uint16_t *>(code + cap);   // [cap] rank inside the bucket; later: sorted position of an env to reset
+    uint16_t *perm = rank + cap;                                 // [cap] runnable envs, sorted
+    uint16_t *rlist = perm + cap;                                // [cap] envs to reset: el | 0x8000 when its option ran
     __shared__ uint64_t bar;
     __shared__ int sh_stats[8];
     __shared__ int hist[NBUCKET];
-    __shared__ int next_chunk;
+    __shared__ int next_chunk, n_reset;
     __shared__ uint32_t rec_base;
-    __shared__ uint8_t ckey[TILE / 32], order[TILE / 32];   // length class of each runnable chunk; chunks longest first
-    __shared__ uint32_t info[TILE];
-    __shared__ uint16_t perm0[TILE];
-    uint16_t *const perm = perm0;                            // the class order replaces the option order (dead after phase 1)
+    __shared__ uint8_t ckey[136], order[136], clen[136];    // per chunk: priority, rank -> chunk, envs (<= 32)
+    __shared__ uint16_t cstart[136];                        // per chunk: first position in perm[]
+    __shared__ int n_chunks;
     const int tid = threadIdx.x, lane = tid & 31;
-    phase_stamp(B, 0);
     if (tid < 8) sh_stats[tid] = 0;
     if (tid < NBUCKET) hist[tid] = 0;
-    if (tid == 0) next_chunk = 0;
+    if (tid == 0) { next_chunk = 0; n_reset = 0; }
+    phase_stamp(B, 0, &next_chunk);
     stage_levels(levels, B.levels, B.n_levels, &bar);      // contains a __syncthreads()
-    phase_stamp(B, 1);
+    phase_stamp(B, 1, &next_chunk);
 
     const int64_t base = B.r_begin + (int64_t)blockIdx.x * tile;
     const int count = (int)min((int64_t)tile, B.r_begin + B.r_count - base);
+    const uint32_t t_now = B.step_counter[0];               // gym steps taken before this call
+    const uint32_t max_steps = B.max_steps > 0 ? (uint32_t)B.max_steps : 0xFFFFFFFFu;
+    const int od = B.obs_dim;
 
-    // Global loads of one phase are issued in batches before their first use: a dependent access costs about 1 us
-    // here (measured with tg_debug_phase_buffer), and one element per thread at a time left the SM waiting on it.
-    // ---- phase 0: sort by option id -------------------------------------------
-    for (int k0 = 0; k0 < count; k0 += 8 * STEP_THREADS) {
-        int av[8];
+    uint32_t st_cnt = 0;                                    // errors | episodes << 8 | successes << 16 | ran << 24
+    int st_ticks = 0, st_ret = 0, st_epsteps = 0;
+
+    // ---- phase A ---------------------------------------------------------------
+    {
+        // 16-byte accesses when this tile's slices start on 16 bytes (base is a multiple of 4 for every tile the
+        // launchers produce; caller-provided arrays may be offset)
+        const bool va = ((reinterpret_cast<uintptr_t>(actions + base) | reinterpret_cast<uintptr_t>(B.plan + base) |
+                          reinterpret_cast<uintptr_t>(B.ep_start + base)) & 15u) == 0;
+        const bool vo = (!reward || (reinterpret_cast<uintptr_t>(reward + base) & 15u) == 0) &&
+                        (!done_out || (reinterpret_cast<uintptr_t>(done_out + base) & 3u) == 0) &&
+                        (!ran_out || (reinterpret_cast<uintptr_t>(ran_out + base) & 3u) == 0) &&
+                        (!avail_out || (reinterpret_cast<uintptr_t>(avail_out + base) & 7u) == 0);
+        for (int el0 = 4 * tid; el0 < count; el0 += 4 * STEP_THREADS) {
+            const int m = min(4, count - el0);
+            const int64_t i0 = base + el0;
+            int av[4]; uint32_t plo[4], phi[4], ev[4];
+            if (va && m == 4) {
+                const int4 a4 = *reinterpret_cast<const int4 *>(actions + i0);
+                const uint4 p01 = *reinterpret_cast<const uint4 *>(B.plan + i0), p23 = *reinterpret_cast<const uint4 *>(B.plan + i0 + 2);
+                const uint4 e4 = *reinterpret_cast<const uint4 *>(B.ep_start + i0);
+                av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+                plo[0] = p01.x; phi[0] = p01.y; plo[1] = p01.z; phi[1] = p01.w; plo[2] = p23.x; phi[2] = p23.y; plo[3] = p23.z; phi[3] = p23.w;
+                ev[0] = e4.x; ev[1] = e4.y; ev[2] = e4.z; ev[3] = e4.w;
+            } else {
 #pragma unroll
-        for (int u = 0; u < 8; u++) { const int el = k0 + u * STEP_THREADS + tid; av[u] = (el < count) ? actions[base + el] : 0; }
+                for (int u = 0; u < 4; u++) {
+                    const uint64_t p = (u < m) ? B.plan[i0 + u] : 0ull;
+                    av[u] = (u < m) ? actions[i0 + u] : TG_NUM_OPTIONS; plo[u] = (uint32_t)p; phi[u] = (uint32_t)(p >> 32);
+                    ev[u] = (u < m) ? B.ep_start[i0 + u] : t_now + 1u;
+                }
+            }
+            uint32_t dn = 0, cd = 0;                                   // 4 done bytes, 4 code bytes
+            uint32_t special = 0;                                      // per element: bit u = reset, bit 4 + u = reference would raise
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int el = k0 + u * STEP_THREADS + tid;
-            if (el < count) {
-                const int ac = ((unsigned)av[u] < (unsigned)TG_NUM_OPTIONS) ? av[u] : TG_NUM_OPTIONS;   // tg:92 raises IndexError; here: not run
-                info[el] = (uint32_t)ac;
-                atomicAdd(&hist[ac], 1);
+            for (int u = 0; u < 4; u++) {
+                const uint32_t a = (uint32_t)av[u] < (uint32_t)TG_NUM_OPTIONS ? (uint32_t)av[u] : 12u;   // tg:92 raises IndexError; here: not run (bit 12 is never set)
+                const uint32_t lo = plo[u];
+                const bool run = (lo >> a) & 1u;
+                // sort key: code-path class major (lanes of a warp then run the same policy and the same branch of
+                // tick()), estimated length minor (longest first).  class of option a: nibble a of 0x332241100 (walk, ladder, drop, jump, interact)
+                const uint32_t lenc = ((a < 4u ? lo >> (PL_LEN + 4u * a) : phi[u] >> (4u * a - 16u)) & 15u);
+                const uint32_t bucket = (uint32_t)((0x332241100ull >> (4u * a)) & 15ull) * 12u + 11u - lenc;
+                const uint32_t steps = t_now + 1u - ev[u];
+                const uint32_t d = run ? 0u : (((lo >> PL_TERM) & 1u) | (steps >= max_steps ? (uint32_t)TG_DONE_TRUNCATED : 0u));
+                dn |= d << (8 * u);
+                cd |= (run ? bucket : 255u) << (8 * u);
+                if (run) rank[el0 + u] = (uint16_t)atomicAdd(&hist[bucket], 1);
+                special |= (d ? 1u : 0u) << u;
+                special |= ((!run && ((a == (uint32_t)TG_DOWN_LEFT && ((lo >> PL_ERR_DL) & 1u)) || (a == (uint32_t)TG_DOWN_RIGHT && ((lo >> PL_ERR_DR) & 1u)))) ? 16u : 0u) << u;
+            }
+            *reinterpret_cast<uint32_t *>(code + el0) = cd;            // el0 is a multiple of 4, cap a multiple of 16
+            if (special) {                                             // rare: episode over (time limit / done), or the reference would raise
+                for (int u = 0; u < m; u++) {
+                    const int64_t i = i0 + u;
+                    if ((special >> (4 + u)) & 1u) {
+                        uint32_t *fw = reinterpret_cast<uint32_t *>(B.core + i) + 1;   // flag the env (target None in the reference)
+                        const uint32_t f = *fw;
+                        if (!(f & (1u << F_ERROR))) { *fw = f | (1u << F_ERROR); st_cnt += 1u; }
+                    }
+                    if ((special >> u) & 1u) {
+                        if (B.auto_reset) rlist[atomicAdd(&n_reset, 1)] = (uint16_t)(el0 + u);      // statistics: when it is reset
+                        else {
+                            st_cnt += (1u << 8) + (((dn >> (8 * u)) & TG_DONE_TERMINATED) ? 1u << 16 : 0u);
+                            st_ret += (int)B.acct[i].y; st_epsteps += (int)(t_now + 1u - ev[u]);
+                        }
+                    }
+                }
+            }
+            if (vo && m == 4) {
+                if (reward) *reinterpret_cast<float4 *>(reward + i0) = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (done_out) *reinterpret_cast<uint32_t *>(done_out + i0) = dn;
+                if (ran_out) *reinterpret_cast<uint32_t *>(ran_out + i0) = 0u;
+                if (avail_out) *reinterpret_cast<ushort4 *>(avail_out + i0) = make_ushort4(plo[0] & 0x1FFu, plo[1] & 0x1FFu, plo[2] & 0x1FFu, plo[3] & 0x1FFu);
+            } else {
+                for (int u = 0; u < m; u++) {
+                    if (reward) reward[i0 + u] = 0.f;
+                    if (done_out) done_out[i0 + u] = (uint8_t)(dn >> (8 * u));
+                    if (ran_out) ran_out[i0 + u] = 0;
+                    if (avail_out) avail_out[i0 + u] = (uint16_t)(plo[u] & 0x1FFu);
+                }
             }
         }
     }
     __syncthreads();
-    if (tid < 32) scan64(hist, lane);
-    __syncthreads();
-    for (int el = tid; el < count; el += STEP_THREADS) perm0[atomicAdd(&hist[info[el]], 1)] = (uint16_t)el;
-    __syncthreads();
-    if (tid < NBUCKET) hist[tid] = 0;
-    __syncthreads();
-    phase_stamp(B, 2);
-
-    // ---- phase 1: classify, in option order -------------------------------------
-    for (int j0 = 0; j0 < count; j0 += 4 * STEP_THREADS) {
-        uint4 cv[4];
-        int elv[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int j = j0 + u * STEP_THREADS + tid;
-            elv[u] = (j < count) ? perm0[j] : -1;
-            if (elv[u] >= 0) cv[u] = B.core[base + elv[u]];
-        }
-#pragma unroll 1
-        for (int u = 0; u < 4; u++) {       // one copy of the classification code: pick the element with selects
-            const int el = (u == 0) ? elv[0] : (u == 1) ? elv[1] : (u == 2) ? elv[2] : elv[3];
-            if (el < 0) continue;
-            const uint4 cu = (u == 0) ? cv[0] : (u == 1) ? cv[1] : (u == 2) ? cv[2] : cv[3];
-            const int64_t i = base + el;
-            const LevelBlob &L = levels[B.level_id ? B.level_id[i] : 0];
-            Env<NI> e;
-            load_core(e, B, i, cu);
-            const int a = (int)info[el];
-            int tcx; bool err;
-            const bool ran = option_setup(e, L, a, tcx, err);
-            // sort key: code-path class major (lanes of a warp then run the same policy and the same branch of
-            // tick()), estimated length minor (longest first); 63 = not runnable
-            int bucket = NBUCKET - 1;
-            if (ran) {
-                const int cls = (a <= TG_GO_RIGHT) ? 0 : (a <= TG_DOWN_LADDER) ? 1 : (a == TG_INTERACT) ? 4 : (a <= TG_DOWN_RIGHT) ? 2 : 3;
-                bucket = cls * 12 + 11 - min(estimate_ticks(e, L, a, tcx) / 10, 11);
-            }
-            info[el] = pack_info(ran, err, tcx, bucket, a);
-            atomicAdd(&hist[bucket], 1);
-        }
-    }
-    __syncthreads();
-    phase_stamp(B, 3);
-    // ---- phase 2: exclusive scan of the 64 class counts (warp 0), scatter the runnable envs, then order their
+    phase_stamp(B, 2, &next_chunk);
+    // ---- sort: exclusive scan of the 64 bucket counts (warp 0), scatter the runnable envs by rank, then order their
     // 32-env chunks longest first across classes (a chunk's first env is its longest: length is the minor key) ----
     if (tid < 32) scan64(hist, lane);
     __syncthreads();
     for (int el = tid; el < count; el += STEP_THREADS) {
-        const uint32_t inf = info[el];
-        if (inf & 1u) perm[atomicAdd(&hist[(inf >> 8) & 63], 1)] = (uint16_t)el;
+        const int c = code[el];
+        if (c != 255) perm[hist[c] + rank[el]] = (uint16_t)el;
     }
-    const int n_run = hist[NBUCKET - 1];                    // exclusive scan: start of bucket 63 (not runnable) = runnable envs
-    const int nrc = (n_run + 31) >> 5;
+    const int n_run = hist[NBUCKET - 1];                    // exclusive scan: start of the (unused) last bucket = runnable envs
+    const int n_idle_rst = n_reset;                         // idle envs to reset; the option lanes append theirs
     __syncthreads();
-    if (tid == STEP_THREADS - 1 && B.sp_count) rec_base = atomicAdd(B.sp_count, (uint32_t)n_run);    // sparse outputs: this tile's block of records
+    if (tid == STEP_THREADS - 1 && B.sp_count && n_run + n_idle_rst > 0)
+        rec_base = atomicAdd(B.sp_count, (uint32_t)(n_run + n_idle_rst));      // sparse outputs: this tile's block of records
+    // Chunks of up to 32 envs that never straddle two classes (a warp whose lanes belong to different classes runs their
+    // code paths one after the other: the chunk at the ladder / drop / jump / interact border took 100 us): per class,
+    // ceil(count / 32) chunks.  Order: drops and jumps first (single lanes on the general tick: the longest chains), then
+    // longest first across classes (a chunk's first env is its longest: length is the minor sort key).
     if (tid < 32) {
-        for (int c = lane; c < nrc; c += 32) ckey[c] = (uint8_t)(11 - ((info[perm[c * 32]] >> 8) & 63u) % 12u);
+        const int cs = lane < 5 ? hist[12 * lane] : n_run, ce = lane < 5 ? hist[12 * (lane + 1)] : n_run;   // class lane = perm[cs .. ce)
+        const int nch = (ce - cs + 31) >> 5;
+        int incl = nch;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+        const int q0 = incl - nch;
+        const int nq = __shfl_sync(0xFFFFFFFFu, incl, 4);
+        for (int t = 0; t < nch; t++) {
+            cstart[q0 + t] = (uint16_t)(cs + 32 * t);
+            clen[q0 + t] = (uint8_t)min(32, ce - cs - 32 * t);
+            ckey[q0 + t] = (uint8_t)(11 - code[perm[cs + 32 * t]] % 12 + ((lane == 2 || lane == 3) ? 12 : 0));
+        }
+        if (lane == 0) n_chunks = nq;
         __syncwarp();
-        for (int c = lane; c < nrc; c += 32) {
+        for (int c = lane; c < nq; c += 32) {
             const int k = ckey[c];
             int r = 0;
-            for (int j = 0; j < nrc; j++) { const int kj = ckey[j]; r += (kj > k || (kj == k && j < c)) ? 1 : 0; }
+            for (int j = 0; j < nq; j++) { const int kj = ckey[j]; r += (kj > k || (kj == k && j < c)) ? 1 : 0; }
             order[r] = (uint8_t)c;
         }
     }
     __syncthreads();
-    phase_stamp(B, 4);
+    const int nrc = n_chunks;
+    phase_stamp(B, 3, &next_chunk);
 
-    uint32_t st_cnt = 0;                                    // errors | episodes << 8 | successes << 16 | ran << 24
-    int st_ticks = 0, st_ret = 0, st_epsteps = 0;
-    const int od = B.obs_dim;
-    float *stage = reinterpret_cast<float *>(smem_raw + (((size_t)B.n_levels * sizeof(LevelBlob) + 15) & ~(size_t)15))
-                   + (size_t)(tid >> 5) * 32 * od;                             // this warp's [32][obs_dim] rows
-    const bool vec_ok = obs && ((reinterpret_cast<uintptr_t>(obs + base * od) & 15u) == 0);    // this tile's rows start on 16 bytes
-
-    // ---- phase 3: one queue of 32-env chunks from a shared counter.  First the runnable envs (class-sorted chunks,
-    // longest first): a lane runs its env's option to termination and puts the state back; info[el] becomes bits
-    // 0-12 ticks, bit 13 env newly flagged, bits 14-17 option id, bit 18 set, bits 19-31 uniforms drawn.  Then every
-    // index-order chunk, for the envs whose option did not run (so this work overlaps the long options above):
-    // time-limit / auto-reset (rare: out of line, through memory) / outputs with contiguous loads and stores.
-    // Observation rows are built in shared memory and leave with full-line stores; the rows of the envs that ran
-    // are rewritten by phase 5.
-    const int nchunks = nrc + ((count + 31) >> 5);
+    // ---- phase B: 32-env chunks of runnable envs (class-sorted, longest first) from a shared counter
     for (;;) {
         int q = 0;
         if (lane == 0) q = atomicAdd(&next_chunk, 1);
         q = __shfl_sync(0xFFFFFFFFu, q, 0);
-        if (q >= nchunks) break;
-        if (q < nrc) {
-            const int j = order[q] * 32 + lane;
-            if (j < n_run) {
-                const int el = perm[j];
-                const uint32_t inf = info[el];
-                const int64_t i = base + el;
-                const LevelBlob &L = levels[B.level_id ? B.level_id[i] : 0];
-                Env<NI> e;
-                uint4 acct;
-                load_env(e, B, i, acct);
-                const int a = (int)((inf >> 14) & 15u);
-                const uint32_t err0 = e.flags & (1u << F_ERROR);
-                const int n = run_option_to_end<TAPE>(e, L, a, (int)((inf >> 2) & 63u) - 8);
-                store_env(e, B, i, acct);
-                const uint32_t newerr = ((e.flags & (1u << F_ERROR)) && !err0) ? 1u : 0u;
-                info[el] = (uint32_t)n | (newerr << 13) | ((uint32_t)a << 14) | (1u << 18) | ((e.draws - e.d0) << 19);
-            }
-            continue;
+        if (q >= nrc) break;
+        const int cq = order[q];
+        const int j = cstart[cq] + lane;
+        unsigned long long chunk_t0 = 0;                                          // debug instrumentation: per-chunk timing
+        if (B.phase_ts && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(chunk_t0) :: "memory");
+        const bool valid = lane < clen[cq];
+        const int el = valid ? perm[j] : 0;
+        const int64_t i = base + el;
+        const int lid = (valid && B.level_id) ? B.level_id[i] : 0;
+        const LevelBlob &L = levels[lid];
+        const int a = valid ? actions[i] : -1;
+        const uint32_t eps = valid ? B.ep_start[i] : 0u;
+        Env<NI> e;
+        uint4 acct;
+        int n, tcx = 0;
+        uint32_t newerr = 0, err0 = 0, drawn_i = 0;
+        if (a == TG_INTERACT) drawn_i = interact_option_mem<TAPE, NI>(B, &L, i);   // whole chunks: interact is its own sort class
+        if (valid) {
+            load_env(e, B, i, acct);
+            if (a == TG_INTERACT) e.d0 = e.draws - drawn_i;
+            else { bool err; option_setup(e, L, a, tcx, err); err0 = e.flags & (1u << F_ERROR); }   // runnable (the plan says so): target column
         }
-        const int el0 = (q - nrc) * 32, el = el0 + lane;
-        const int rows = min(32, count - el0);
-        if (el < count && !((info[el] >> 18) & 1u)) {
-            const uint32_t inf = info[el];
-            const int64_t i = base + el;
-            const int lid = B.level_id ? B.level_id[i] : 0;
-            const LevelBlob &L = levels[lid];
-            Env<NI> e;
-            uint4 cv = B.core[i];
-            uint4 acct = B.acct[i];
-            load_core(e, B, i, cv);
-            e.angles = B.angles + i; e.n = B.n;
-            if ((inf & 2u) && !(e.flags & (1u << F_ERROR))) {                // the reference would raise (target None)
-                e.flags |= 1u << F_ERROR; st_cnt += 1u;
-                cv.y = e.flags; B.core[i] = cv;
-            }
-            acct.z += 1u;
-            const bool term = is_done(e, L);
-            const bool trunc = B.max_steps > 0 && acct.z >= (uint32_t)B.max_steps;
-            const int d = (term ? TG_DONE_TERMINATED : 0) | (trunc ? TG_DONE_TRUNCATED : 0);
-            if (d) {
-                st_cnt += (1u << 8) + (term ? 1u << 16 : 0u); st_ret += (int)acct.y; st_epsteps += (int)acct.z;
-                if (B.auto_reset) {
-                    acct.y = 0; acct.z = 0;
-                    B.acct[i] = acct;
-                    reset_in_memory<TAPE, NI>(B, &L, i, 0u);
-                    acct = B.acct[i];
-                    load_core(e, B, i);
-                }
-            }
-            B.acct[i] = acct;
-            if (B.sp_count) {                                                // sparse outputs: only an env that was reset (or stays done) reports
-                if (d) {
-                    uint32_t *rec = B.sp_recs + (size_t)atomicAdd(B.sp_count, 1u) * B.sp_words;
-                    rec[0] = (uint32_t)i; rec[1] = 0u; rec[2] = (uint32_t)d;
-                    write_obs(e, L, B.obs_lut + (size_t)lid * 2 * OBS_LUT_N, reinterpret_cast<float *>(rec + 3), od);
-                }
-            }
-            if (obs) write_obs(e, L, B.obs_lut + (size_t)lid * 2 * OBS_LUT_N, stage + lane * od, od);
-            if (reward) reward[i] = 0.0f;
-            if (done_out) done_out[i] = (uint8_t)d;
-            if (ran_out) ran_out[i] = (uint8_t)0;
-            if (avail_out) avail_out[i] = (uint16_t)available_bits(e, L);
+        unsigned long long chunk_t1 = 0, chunk_t2 = 0, chunk_t3 = 0;
+        if (B.phase_ts && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(chunk_t1) : "r"(tcx + (int)acct.x) : "memory");
+        n = run_option_to_end<TAPE, NI, false>(e, L, a, tcx, valid && a != TG_INTERACT);
+        if (B.phase_ts && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(chunk_t2) : "r"(n) : "memory");
+        if (!valid) continue;
+        if (a == TG_INTERACT) n = 1;
+        else newerr = ((e.flags & (1u << F_ERROR)) && !err0) ? 1u : 0u;
+        st_cnt += newerr + (1u << 24);
+        st_ticks += n;
+        const bool jump = a >= TG_JUMP_LEFT;
+        const int r = -n - (jump ? 4 : 0);                                        // impl:15-16: -1 per tick, JUMP tick -5
+        acct.y = (uint32_t)((int)acct.y + r);
+        const uint32_t steps = t_now + 1u - eps;
+        const bool term = is_done(e, L);
+        const uint32_t d = (term ? TG_DONE_TERMINATED : 0) | (steps >= max_steps ? TG_DONE_TRUNCATED : 0);
+        if (d) { st_cnt += (1u << 8) + (term ? 1u << 16 : 0u); st_ret += (int)acct.y; st_epsteps += (int)steps; }
+        if (d && B.auto_reset) {                                                  // reset in phase C (full warps)
+            acct.y = 0; acct.z = pack_pending(e.draws - e.d0, n, jump, d);
+            store_env(e, B, i, acct);
+            rank[el] = (uint16_t)j;
+            rlist[atomicAdd(&n_reset, 1)] = (uint16_t)(el | 0x8000);
+        } else {
+            store_env(e, B, i, acct);
+            const uint64_t plan = plan_of(e, L);
+            B.plan[i] = plan;
+            if (B.phase_ts && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(chunk_t3) : "r"((uint32_t)plan) : "memory");
+            uint32_t *rec = B.sp_count ? B.sp_recs + (size_t)(rec_base + (uint32_t)j) * B.sp_words : nullptr;
+            if (rec) { rec[0] = (uint32_t)i; rec[1] = __float_as_uint((float)r); rec[2] = d | 256u; }
+            if (obs || rec)
+                write_obs(e, L, B.obs_lut + (size_t)lid * 2 * OBS_LUT_N, obs ? obs + i * od : nullptr, od,
+                          rec ? reinterpret_cast<float *>(rec + 3) : nullptr);
+            if (avail_out) avail_out[i] = (uint16_t)(plan & 0x1FFu);
         }
-        if (obs) {
-            __syncwarp();
-            float *dst = obs + (base + el0) * od;
-            const int nf = rows * od;
-            if (vec_ok && (nf & 3) == 0) {
-                for (int k = lane; k < (nf >> 2); k += 32) reinterpret_cast<float4 *>(dst)[k] = reinterpret_cast<const float4 *>(stage)[k];
-            } else {
-                for (int k = lane; k < nf; k += 32) dst[k] = stage[k];
-            }
-            __syncwarp();
+        if (reward) reward[i] = (float)r;
+        if (done_out) done_out[i] = (uint8_t)d;
+        if (ran_out) ran_out[i] = (uint8_t)1;
+        if (B.phase_ts && lane == 0 && q < 128) {                                 // [grid][8] phase stamps, then [grid][128][4] chunks
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1) :: "memory");
+            unsigned long long *ct = B.phase_ts + (size_t)gridDim.x * 8 + ((size_t)blockIdx.x * 128 + (size_t)q) * 4;
+            ct[0] = chunk_t0; ct[1] = (t1 - chunk_t0) | ((unsigned long long)(code[el] / 12) << 32) | ((unsigned long long)n << 40);
+            ct[2] = (chunk_t1 - chunk_t0) | ((chunk_t2 - chunk_t1) << 32);
+            ct[3] = chunk_t3 ? ((chunk_t3 - chunk_t2) | ((t1 - chunk_t3) << 32)) : 0ull;
         }
     }
-    __syncthreads();      // every option has run; the rows written above are ordered before the ones written below
-    phase_stamp(B, 5);
+    phase_stamp(B, 4, &next_chunk);
+    __syncthreads();
+    phase_stamp(B, 5, &next_chunk);
 
-    // ---- phase 5: the envs whose option ran: reward / done / time-limit / auto-reset / outputs ----
-    for (int j = tid; j < n_run; j += STEP_THREADS) {
-        const int el = perm[j];
-        const uint32_t inf = info[el];
+    // ---- phase C: the envs whose episode ended (auto_reset): reset_game (impl:55-73) with full warps ----
+    const int n_rst = n_reset;
+    for (int k = tid; k < n_rst; k += STEP_THREADS) {
+        const uint32_t v = rlist[k];
+        const int el = (int)(v & 0x7FFFu);
         const int64_t i = base + el;
         const int lid = B.level_id ? B.level_id[i] : 0;
         const LevelBlob &L = levels[lid];
         Env<NI> e;
-        uint4 acct = B.acct[i];
-        load_core(e, B, i);
-        e.angles = B.angles + i; e.n = B.n;
-        const int a = (int)((inf >> 14) & 15u);
-        const int n = (int)(inf & 0x1FFFu);
-        st_cnt += ((inf >> 13) & 1u) + (1u << 24);
-        st_ticks += n;
-        const int r = -n - ((a >= TG_JUMP_LEFT) ? 4 : 0);                    // impl:15-16: -1 per tick, JUMP tick -5
-        acct.y = (uint32_t)((int)acct.y + r);
-        acct.z += 1u;
-        const bool term = is_done(e, L);
-        const bool trunc = B.max_steps > 0 && acct.z >= (uint32_t)B.max_steps;
-        const int d = (term ? TG_DONE_TERMINATED : 0) | (trunc ? TG_DONE_TRUNCATED : 0);
-        if (d) {
-            st_cnt += (1u << 8) + (term ? 1u << 16 : 0u); st_ret += (int)acct.y; st_epsteps += (int)acct.z;
-            if (B.auto_reset) {
-                acct.y = 0; acct.z = 0;
-                B.acct[i] = acct;
-                reset_in_memory<TAPE, NI>(B, &L, i, inf >> 19);
-                acct = B.acct[i];
-                load_core(e, B, i);
-            }
+        uint4 acct;
+        load_env(e, B, i, acct);
+        uint32_t drawn = 0, rec_reward = 0, rec_flags, slot;
+        if (v & 0x8000u) {                                                        // its option ran: statistics already counted
+            const uint32_t z = acct.z;
+            drawn = z & 0xFFFFu;
+            const int r = -(int)((z >> 16) & 0x1FFFu) - (((z >> 29) & 1u) ? 4 : 0);
+            rec_reward = __float_as_uint((float)r); rec_flags = (z >> 30) | 256u;
+            slot = rank[el];
+        } else {
+            const uint32_t steps = t_now + 1u - B.ep_start[i];
+            const bool term = (B.plan[i] >> PL_TERM) & 1ull;
+            rec_flags = (term ? TG_DONE_TERMINATED : 0) | (steps >= max_steps ? TG_DONE_TRUNCATED : 0);
+            st_cnt += (1u << 8) + (term ? 1u << 16 : 0u); st_ret += (int)acct.y; st_epsteps += (int)steps;
+            slot = (uint32_t)(n_run + k);                                         // k < n_idle_rst: the list starts with the idle envs
         }
-        B.acct[i] = acct;
-        if (B.sp_count) {                                                    // sparse outputs: every env that ran reports
-            uint32_t *rec = B.sp_recs + (size_t)(rec_base + (uint32_t)j) * B.sp_words;
-            rec[0] = (uint32_t)i; rec[1] = __float_as_uint((float)r); rec[2] = (uint32_t)d | 256u;
-            write_obs(e, L, B.obs_lut + (size_t)lid * 2 * OBS_LUT_N, reinterpret_cast<float *>(rec + 3), od);
-        }
-        if (obs) write_obs(e, L, B.obs_lut + (size_t)lid * 2 * OBS_LUT_N, obs + i * od, od);
-        if (reward) reward[i] = (float)r;
-        if (done_out) done_out[i] = (uint8_t)d;
-        if (ran_out) ran_out[i] = (uint8_t)1;
-        if (avail_out) avail_out[i] = (uint16_t)available_bits(e, L);
+        acct.y = 0; acct.z = 0;
+        // the Philox blocks of a call are numbered from the call's first draw (draw_w): the reset continues the numbering
+        e.d0 = e.draws - drawn;
+        if (!TAPE && (drawn & 3u)) { const uint4 o = philox_block(e.d0, drawn >> 2, e.id_lo, e.id_hi, e.key0, e.key1); e.w0 = o.x; e.w1 = o.y; e.w2 = o.z; e.w3 = o.w; }
+        reset_env<TAPE>(e, L);
+        store_env(e, B, i, acct);
+        const uint64_t plan = plan_of(e, L);
+        B.plan[i] = plan;
+        B.ep_start[i] = t_now + 1u;
+        uint32_t *rec = B.sp_count ? B.sp_recs + (size_t)(rec_base + slot) * B.sp_words : nullptr;
+        if (rec) { rec[0] = (uint32_t)i; rec[1] = rec_reward; rec[2] = rec_flags; }
+        if (obs || rec)
+            write_obs(e, L, B.obs_lut + (size_t)lid * 2 * OBS_LUT_N, obs ? obs + i * od : nullptr, od,
+                      rec ? reinterpret_cast<float *>(rec + 3) : nullptr);
+        if (avail_out) avail_out[i] = (uint16_t)(plan & 0x1FFu);
     }
-    phase_stamp(B, 6);
+    phase_stamp(B, 6, &next_chunk);
     int st[8];
     st[ST_EPISODES] = (st_cnt >> 8) & 255; st[ST_SUCCESS] = (st_cnt >> 16) & 255; st[ST_RETURN] = st_ret; st[ST_EPSTEPS] = st_epsteps;
     st[ST_TICKS] = st_ticks; st[ST_RAN] = st_cnt >> 24; st[ST_ERRORS] = st_cnt & 255;
     st[ST_STEPS] = (tid == 0) ? count : 0;                  // every env of the tile takes exactly one gym step
     stats_accumulate(sh_stats, B.stats, st);
-    phase_stamp(B, 7);
+    phase_stamp(B, 7, &next_chunk);
+    finish_launch(B);
+}
+
+// Observation rows of every env (impl:368-378) from the stored state: follows a step kernel whose caller's `obs` is
+// not known to hold the previous observations, and serves tg_reset.  Rows are built in shared memory and leave
+// with full-line stores.
+template <int NI>
+__global__ void __launch_bounds__(256)
+tg_obs_kernel(const __grid_constant__ BatchView B, float *__restrict__ obs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LevelBlob *levels = reinterpret_cast<LevelBlob *>(smem_raw);
+    float *stage = reinterpret_cast<float *>(smem_raw + (((size_t)B.n_levels * sizeof(LevelBlob) + 15) & ~(size_t)15));   // [256][obs_dim]
+    __shared__ uint64_t bar;
+    stage_levels(levels, B.levels, B.n_levels, &bar);
+    const int od = B.obs_dim;
+    const int64_t i0 = B.r_begin + (int64_t)blockIdx.x * 256, i = i0 + threadIdx.x;
+    const int rows = (int)min((int64_t)256, B.r_begin + B.r_count - i0);
+    if ((int)threadIdx.x < rows) {
+        const int lid = B.level_id ? B.level_id[i] : 0;
+        Env<NI> e;
+        load_core(e, B, i);
+        e.angles = B.angles + i; e.n = B.n;
+        write_obs(e, levels[lid], B.obs_lut + (size_t)lid * 2 * OBS_LUT_N, stage + threadIdx.x * od, od);
+    }
+    __syncthreads();
+    float *dst = obs + i0 * od;
+    const int nf = rows * od;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && (nf & 3) == 0) {
+        for (int k = threadIdx.x; k < (nf >> 2); k += 256) reinterpret_cast<float4 *>(dst)[k] = reinterpret_cast<const float4 *>(stage)[k];
+    } else {
+        for (int k = threadIdx.x; k < nf; k += 256) dst[k] = stage[k];
+    }
 }
 
 template <bool TAPE, int NI>
@@ -390,26 +462,20 @@ tg_reset_kernel(BatchView B, const uint8_t *__restrict__ mask, float *__restrict
     if (!mask || mask[i]) {
         e.flags &= ~(1u << F_ERROR);
         reset_env<TAPE>(e, L);
-        acct.y = 0; acct.z = 0;
+        acct.y = 0;
         store_env(e, B, i, acct);
+        B.plan[i] = plan_of(e, L);
+        B.ep_start[i] = B.step_counter[0];                 // the next gym step is the first of the new episode
     }
     if (obs) write_obs(e, L, B.obs_lut + (size_t)(B.level_id ? B.level_id[i] : 0) * 2 * OBS_LUT_N, obs + i * B.obs_dim, B.obs_dim);
 }
 
-template <int NI>
-__global__ void __launch_bounds__(AUX_THREADS)
+// TreasureGame.available_mask (tg:83-89): the nine can_run bits live in the env's plan word
+__global__ void __launch_bounds__(256)
 tg_mask_kernel(BatchView B, uint8_t *__restrict__ mask) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    LevelBlob *levels = reinterpret_cast<LevelBlob *>(smem_raw);
-    __shared__ uint64_t bar;
-    stage_levels(levels, B.levels, B.n_levels, &bar);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B.n) return;
-    const LevelBlob &L = levels[B.level_id ? B.level_id[i] : 0];
-    Env<NI> e;
-    uint4 acct;
-    load_env(e, B, i, acct);
-    const uint32_t m = available_bits(e, L);
+    const uint32_t m = (uint32_t)(B.plan[i] & 0x1FFull);
 #pragma unroll
     for (int k = 0; k < TG_NUM_OPTIONS; k++) mask[i * TG_NUM_OPTIONS + k] = (m >> k) & 1u;
 }
@@ -428,6 +494,7 @@ tg_primitive_kernel(BatchView B, const int32_t *__restrict__ actions, float *__r
     if (threadIdx.x < 8) sh_stats[threadIdx.x] = 0;
     stage_levels(levels, B.levels, B.n_levels, &bar);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t_now = B.step_counter[0];
     int st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (i < B.n) {
         const LevelBlob &L = levels[B.level_id ? B.level_id[i] : 0];
@@ -439,22 +506,24 @@ tg_primitive_kernel(BatchView B, const int32_t *__restrict__ actions, float *__r
         tick<TAPE>(e, L, a);
         const int r = (a == A_JUMP) ? -5 : -1;                               // impl:15-16,356-359
         acct.y = (uint32_t)((int)acct.y + r);
-        acct.z += 1u;
+        const uint32_t steps = t_now + 1u - B.ep_start[i];
         const bool term = is_done(e, L);
-        const bool trunc = B.max_steps > 0 && acct.z >= (uint32_t)B.max_steps;
+        const bool trunc = B.max_steps > 0 && steps >= (uint32_t)B.max_steps;
         const int d = (term ? TG_DONE_TERMINATED : 0) | (trunc ? TG_DONE_TRUNCATED : 0);
         st[ST_TICKS] = 1; st[ST_RAN] = 1; st[ST_STEPS] = 1;
         st[ST_ERRORS] = ((e.flags & (1u << F_ERROR)) && !err0) ? 1 : 0;
         if (d) {
-            st[ST_EPISODES] = 1; st[ST_SUCCESS] = term; st[ST_RETURN] = (int)acct.y; st[ST_EPSTEPS] = (int)acct.z;
-            if (B.auto_reset) { reset_env<TAPE>(e, L); acct.y = 0; acct.z = 0; }
+            st[ST_EPISODES] = 1; st[ST_SUCCESS] = term; st[ST_RETURN] = (int)acct.y; st[ST_EPSTEPS] = (int)steps;
+            if (B.auto_reset) { reset_env<TAPE>(e, L); acct.y = 0; B.ep_start[i] = t_now + 1u; }
         }
         store_env(e, B, i, acct);
+        B.plan[i] = plan_of(e, L);
         if (obs) write_obs(e, L, B.obs_lut + (size_t)(B.level_id ? B.level_id[i] : 0) * 2 * OBS_LUT_N, obs + i * B.obs_dim, B.obs_dim);
         if (reward) reward[i] = (float)r;
         if (done_out) done_out[i] = (uint8_t)d;
     }
     stats_accumulate(sh_stats, B.stats, st);
+    finish_launch(B);
 }
 
 template <bool TAPE, int NI>
@@ -472,6 +541,7 @@ tg_init_with_state_kernel(BatchView B, const double *__restrict__ states, const 
     load_env(e, B, i, acct);
     init_with_state_env<TAPE>(e, L, states + i * B.obs_dim);
     store_env(e, B, i, acct);
+    B.plan[i] = plan_of(e, L);
 }
 
 // ---- state get / set (unpacked view, strides = TG_MAX_*) -------------------
@@ -493,7 +563,10 @@ __global__ void tg_get_state_kernel(BatchView B, tg_state_view v) {
         const int len = bag_len(f);
         for (int j = 0; j < TG_MAX_ITEMS; j++) v.bag[i * TG_MAX_ITEMS + j] = (j < len) ? (int)((f >> (F_BAGORD + 2 * j)) & 3u) : -1;
     }
-    if (v.acct) { v.acct[i * 3] = (int)a.y; v.acct[i * 3 + 1] = a.z; v.acct[i * 3 + 2] = ((f >> F_ERROR) & 1u) | (core_sticky(c.x) << 1); }
+    if (v.acct) {
+        v.acct[i * 3] = (int)a.y; v.acct[i * 3 + 1] = B.step_counter[0] - B.ep_start[i];
+        v.acct[i * 3 + 2] = ((f >> F_ERROR) & 1u) | (core_sticky(c.x) << 1);
+    }
 }
 
 __global__ void tg_set_state_kernel(BatchView B, tg_state_view v) {
@@ -537,12 +610,16 @@ __global__ void tg_set_state_kernel(BatchView B, tg_state_view v) {
         f |= (uint32_t)len << F_BAGLEN;
     }
     if (v.acct) {
-        a.y = (uint32_t)(int)v.acct[i * 3]; a.z = (uint32_t)v.acct[i * 3 + 1];
+        a.y = (uint32_t)(int)v.acct[i * 3];
+        B.ep_start[i] = B.step_counter[0] - (uint32_t)v.acct[i * 3 + 1];
         f = (f & ~(1u << F_ERROR)) | (((v.acct[i * 3 + 2] & 1) ? 1u : 0u) << F_ERROR);
         c.x = pack_player(core_px(c.x), hi16(c.x), (uint32_t)(v.acct[i * 3 + 2] >> 1));
     }
     c.y = f;
     B.core[i] = c; B.acct[i] = a;
+    uint2 h = make_uint2(0u, 0u);
+    if (B.items23) h = B.items23[i];
+    B.plan[i] = compute_plan<4>(&B.levels[B.level_id ? B.level_id[i] : 0], pack_player(core_px(c.x), hi16(c.x), 0u), f, c.z, c.w, h.x, h.y);
 }
 
 // ---------------------------------------------------------------------------
@@ -550,48 +627,34 @@ __global__ void tg_set_state_kernel(BatchView B, tg_state_view v) {
 // ---------------------------------------------------------------------------
 static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 static inline size_t level_smem(const BatchView &B) { return (size_t)B.n_levels * sizeof(LevelBlob); }
-// step kernel: level blobs + one [32][obs_dim] float staging area per warp for the coalesced observation rows
-static inline size_t step_smem(const BatchView &B) {
-    return ((level_smem(B) + 15) & ~(size_t)15) + (size_t)(STEP_THREADS / 32) * 32 * B.obs_dim * sizeof(float);
-}
-
-template <bool TAPE, int NI, int TILE>
-static cudaError_t step_tile(const BatchView &B, int tile, const int32_t *a, float *obs, float *rew, uint8_t *done,
-                             uint8_t *ran, uint16_t *avail, cudaStream_t s) {
-    const size_t smem = step_smem(B);
-    {   // static + dynamic shared memory can pass the default 48 KB (large tiles, many layouts): opt in once per size
-        static size_t allowed = 0;
-        if (smem > allowed) {
-            cudaError_t r = cudaFuncSetAttribute(tg_step_kernel<TAPE, NI, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (r != cudaSuccess) return r;
-            allowed = smem;
-        }
-    }
-    tg_step_kernel<TAPE, NI, TILE><<<grid_for(B.r_count, tile), STEP_THREADS, step_smem(B), s>>>(B, tile, a, obs, rew, done, ran, avail);
-    return cudaGetLastError();
-}
+// step kernel: level blobs + the tile's sort arrays (code u8, rank / perm / reset list u16)
+static inline size_t step_smem(const BatchView &B, int cap) { return ((level_smem(B) + 15) & ~(size_t)15) + (size_t)cap * 7; }
 
 template <bool TAPE, int NI>
 static cudaError_t step_impl(const BatchView &B, int tile, const int32_t *a, float *obs, float *rew, uint8_t *done,
                              uint8_t *ran, uint16_t *avail, cudaStream_t s) {
-    if (tile <= 256) return step_tile<TAPE, NI, 256>(B, tile, a, obs, rew, done, ran, avail, s);     // capacity of the shared arrays
-    if (tile <= 1024) return step_tile<TAPE, NI, 1024>(B, tile, a, obs, rew, done, ran, avail, s);
-    return step_tile<TAPE, NI, 4096>(B, tile, a, obs, rew, done, ran, avail, s);
+    const int cap = (tile + 15) & ~15;
+    const size_t smem = step_smem(B, cap);
+    if (smem > 40 * 1024) {   // static + dynamic shared memory can pass the default 48 KB (many layouts): opt in, once per size and device
+        static size_t allowed[MAX_DEVICES] = {};
+        const int dslot = device_slot();
+        if (smem > allowed[dslot]) {
+            cudaError_t r = cudaFuncSetAttribute(tg_step_kernel<TAPE, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (r != cudaSuccess) return r;
+            allowed[dslot] = smem;
+        }
+    }
+    tg_step_kernel<TAPE, NI><<<grid_for(B.r_count, tile), STEP_THREADS, smem, s>>>(B, tile, cap, a, obs, rew, done, ran, avail);
+    return cudaGetLastError();
 }
 
 // Tile size: large tiles sort better (more runnable envs per tile -> fuller warps); small tiles give more
 // CTAs.  The grid is sized in whole "slots": 148 SMs x 3 resident CTAs = 444 CTAs run at once, so the tile is
 // n / (444 * waves) rounded up (2364 envs for a 1,048,576-env step) -- with fixed 2048-env tiles and 4 CTAs per SM a
 // step had 512 CTAs, 68 SMs held four of them and 80 SMs three.  Smaller batches aim for two, then one CTA per SM slot.  TG_STEP_TILE overrides.
-int pick_step_tile(int64_t n) {
-    static int forced = -1, slots = 0;
-    if (forced < 0) { const char *v = getenv("TG_STEP_TILE"); forced = v ? atoi(v) : 0; }
+int pick_step_tile(int64_t n, int forced) {
     if (forced >= 32 && forced <= 4096) return (forced + 3) / 4 * 4;
-    if (!slots) {
-        int dev = 0, sms = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        slots = sms * TG_STEP_MIN_BLOCKS;
-    }
+    const int slots = device_sm_count() * TG_STEP_MIN_BLOCKS;
     const int64_t cap = 4096;
     int64_t ctas;
     if (n >= (int64_t)slots * 512) ctas = (n + slots * cap - 1) / (slots * cap) * slots;      // whole waves of full occupancy
@@ -604,10 +667,10 @@ int pick_step_tile(int64_t n) {
     return (int)tile;
 }
 
-cudaError_t launch_step(const BatchView &B, int ni, const int32_t *a, float *obs, float *rew, uint8_t *done,
+cudaError_t launch_step(const BatchView &B, int ni, int forced_tile, const int32_t *a, float *obs, float *rew, uint8_t *done,
                         uint8_t *ran, uint16_t *avail, cudaStream_t s) {
     const bool tape = B.tape != nullptr;
-    const int tile = pick_step_tile(B.r_count);
+    const int tile = pick_step_tile(B.r_count, forced_tile);
     if (ni <= 2) return tape ? step_impl<true, 2>(B, tile, a, obs, rew, done, ran, avail, s) : step_impl<false, 2>(B, tile, a, obs, rew, done, ran, avail, s);
     return tape ? step_impl<true, 4>(B, tile, a, obs, rew, done, ran, avail, s) : step_impl<false, 4>(B, tile, a, obs, rew, done, ran, avail, s);
 }
@@ -655,9 +718,24 @@ cudaError_t launch_init_with_state(const BatchView &B, int ni, const double *sta
 }
 
 cudaError_t launch_mask(const BatchView &B, int ni, uint8_t *mask, cudaStream_t s) {
-    const unsigned g = grid_for(B.n, AUX_THREADS);
-    if (ni <= 2) tg_mask_kernel<2><<<g, AUX_THREADS, level_smem(B), s>>>(B, mask);
-    else tg_mask_kernel<4><<<g, AUX_THREADS, level_smem(B), s>>>(B, mask);
+    tg_mask_kernel<<<grid_for(B.n, 256), 256, 0, s>>>(B, mask);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_obs(const BatchView &B, int ni, float *obs, cudaStream_t s) {
+    const size_t smem = ((level_smem(B) + 15) & ~(size_t)15) + (size_t)256 * B.obs_dim * sizeof(float);
+    if (smem > 40 * 1024) {
+        static size_t allowed[MAX_DEVICES][2] = {};
+        const int dslot = device_slot(), v = ni <= 2 ? 0 : 1;
+        if (smem > allowed[dslot][v]) {
+            cudaError_t r = ni <= 2 ? cudaFuncSetAttribute(tg_obs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                    : cudaFuncSetAttribute(tg_obs_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (r != cudaSuccess) return r;
+            allowed[dslot][v] = smem;
+        }
+    }
+    if (ni <= 2) tg_obs_kernel<2><<<grid_for(B.r_count, 256), 256, smem, s>>>(B, obs);
+    else tg_obs_kernel<4><<<grid_for(B.r_count, 256), 256, smem, s>>>(B, obs);
     return cudaGetLastError();
 }
 

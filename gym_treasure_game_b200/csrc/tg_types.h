@@ -51,6 +51,10 @@ struct alignas(16) LevelBlob {
     uint8_t handle_obj[4], bolt_obj[4], item_obj[4], door_obj[8];   // object (file-order) index of each
     uint8_t trig_src[TG_MAX_TRIGGERS];   // object index | value << 7, file order (objs.py:65-71)
     uint8_t trig_dst[TG_MAX_TRIGGERS];
+    // the same table grouped by source: the triggers registered for (object o, value v) are trig_list[trig_begin[2o+v] ..
+    // trig_begin[2o+v+1]) in file order, each entry the target as object index | value << 7 (process_trigger walks only these)
+    uint8_t trig_begin[2 * TG_MAX_OBJECTS + 8];
+    uint8_t trig_list[TG_MAX_TRIGGERS];
     float inv_w, inv_h;                  // unused by parity paths (obs divides in double)
     uint32_t pad_[2];
     // observation program (impl:368-378): obs slot k = OP_* << 4 | index (handle / bolt / item number)
@@ -60,6 +64,8 @@ struct alignas(16) LevelBlob {
     uint32_t row_solid[TSTRIDE];         // WALL                                          -> can_go_left/right
     uint32_t row_ladder[TSTRIDE];        // LADDER                                        -> can_go_up/down
     uint32_t row_static_obj[TSTRIDE];    // a handle or bolt lives in the cell (is_object_at, impl:402-409)
+    uint32_t col_nonopen[TSTRIDE];       // column profiles of the same tables (bit = padded row): the ladder options never
+    uint32_t col_ladder[TSTRIDE];        //   change playerx, so their probes look at fixed columns (door cells cleared)
     uint8_t row_lut[TSTRIDE];            // 0 = no door in this row, else 1 + index into door_lut
     uint32_t door_lut[TG_MAX_DOORS][64]; // [rows with doors][closed-door bits] -> column bits of the closed doors of the row
 };
@@ -70,6 +76,15 @@ static_assert(sizeof(LevelBlob) % 16 == 0, "LevelBlob must be a multiple of 16 b
 enum : int { OP_PX = 0, OP_PY, OP_ANGLE, OP_BOLT, OP_IX, OP_IY, OP_ZERO };
 constexpr int OBS_LUT_N = TG_MAX_GRID * TG_CELL_PX + TG_CELL_PX;
 
+// Plan word per env (BatchView::plan): everything the step kernel needs to know about an env whose option does not
+// run, derived from the env's state whenever that state changes (tg_device.cuh compute_plan), so that an idle env
+// costs the step kernel one 8-byte load instead of its 16-byte state record and a 9-way can_run switch:
+//   bits 0-8   can_run of option k (tg:83-89 available_mask)
+//   bit  9     done: gold in the bag and the player in row 0 (tg:95)
+//   bits 10-11 down_left / down_right would raise in the reference (target row None, opts:213-221)
+//   bits 16+4k estimated length class of option k (0..11, estimate / 10 ticks): sort key only, any value is correct
+constexpr int PL_TERM = 9, PL_ERR_DL = 10, PL_ERR_DR = 11, PL_LEN = 16;
+
 // stats vector slots (tg_stats)
 enum : int { ST_EPISODES = 0, ST_SUCCESS, ST_RETURN, ST_EPSTEPS, ST_TICKS, ST_RAN, ST_STEPS, ST_ERRORS };
 
@@ -79,7 +94,13 @@ struct BatchView {
     int64_t first_env_id;
     int64_t r_begin, r_count;   // env range one step launch covers ([0, n) unless tg_step_host pipelines chunks)
     uint4 *core;          // [N]  x=pos(px | py<<16)  y=flags  z=item0 (x | y<<16)  w=item1
-    uint4 *acct;          // [N]  x=draws  y=ep_return  z=ep_steps  w=total_actions
+    uint4 *acct;          // [N]  x=draws  y=ep_return  z=spare  w=total_actions
+    uint64_t *plan;       // [N]  see PL_* above
+    uint32_t *ep_start;   // [N]  index (value of *step_counter) of the first gym step of the env's current episode:
+                          //      episode length so far = *step_counter - ep_start, no per-step write for idle envs
+    uint32_t *step_counter;   // [2] device words: [0] gym steps every env of the batch has taken (one per tg_step /
+                              //     tg_primitive_step call), [1] CTA ticket of the running launch
+    int32_t advance;      // this launch is the last one of its API call: its last CTA increments step_counter[0]
     uint2 *items23;       // [N]  items 2,3 (NULL when every level has <= 2 items)
     double *angles;       // [TG_MAX_HANDLES][N]
     const uint8_t *level_id;   // [N] or NULL

@@ -110,6 +110,9 @@ class VectorTreasureGame:
         self._avail = None
         self._mask = None
         self._stats = torch.zeros((8,), dtype=torch.int64, device=d)
+        # the observation buffer lives as long as this object and only the library writes it: steps update just the
+        # rows of the envs whose state changed (tg_bind_obs).  Results are views: clone before modifying them.
+        check(self._L.tg_bind_obs(self._h, _ptr(self._obs)))
         self._tape = None
         self._host = None
 
@@ -158,7 +161,12 @@ class VectorTreasureGame:
 
     def step_raw(self, actions: torch.Tensor):
         """Hot-loop variant: no tensor post-processing; returns the raw output buffers
-        ``(obs, reward, done_bits, ran)``."""
+        ``(obs, reward, done_bits, ran)``.  ``actions`` must already be a contiguous int32 tensor of shape
+        (N,) on this env's device (``step`` converts; this one only checks)."""
+        if actions.dtype is not torch.int32 or actions.device != self.device or not actions.is_contiguous() \
+                or actions.numel() != self.num_envs:
+            raise ValueError("step_raw needs a contiguous int32 tensor of %d actions on %s (got %s %s on %s)"
+                             % (self.num_envs, self.device, actions.dtype, tuple(actions.shape), actions.device))
         check(self._L.tg_step(self._h, _ptr(actions), _ptr(self._obs), _ptr(self._reward), _ptr(self._done),
                               _ptr(self._ran), None, self._stream()))
         return self._obs, self._reward, self._done, self._ran
@@ -217,6 +225,8 @@ class VectorTreasureGame:
             out = torch.empty((count,) + self.frame_shape, dtype=torch.uint8, device=self.device)
         elif out.shape != (count,) + self.frame_shape or out.dtype != torch.uint8 or not out.is_contiguous():
             raise ValueError("out must be a contiguous uint8 tensor of shape %s" % ((count,) + self.frame_shape,))
+        if out.device != self.device or out.data_ptr() % 16:
+            raise ValueError("out must live on %s and start on a 16-byte boundary (the renderer writes with bulk stores)" % self.device)
         check(self._L.tg_render(self._h, first, count, _ptr(out), self._stream()))
         return out
 
@@ -351,6 +361,10 @@ class VectorTreasureGame:
         a, b = C.c_int64(0), C.c_int64(0)
         self._L.tg_host_traffic(self._h, C.byref(a), C.byref(b))
         return int(a.value), int(b.value)
+
+    def set_step_tile(self, tile: int = 0) -> None:
+        """Tuning / test hook (``tg_debug_set_step_tile``): envs per step-kernel CTA, 0 = automatic."""
+        check(self._L.tg_debug_set_step_tile(self._h, int(tile)))
 
     @property
     def launch_count(self) -> int:

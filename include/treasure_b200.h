@@ -142,9 +142,17 @@ int tg_reset(tg_env *env, const uint8_t *mask, float *obs, void *stream);
  *   (TG_DONE_* bits); ran DEV [N] u8 or NULL; avail DEV [N] u16 or NULL: 9-bit available mask of
  *   the state *after* the step (bit k = option k runnable; treasure_game.py:83-89).
  * With auto_reset, an env whose episode ended is reset inside the call and obs holds the first
- * observation of the new episode. */
+ * observation of the new episode.
+ * Observation rows: an option that cannot run leaves its env untouched (_option.py:22-23), so its row does not
+ * change.  When `obs` is the buffer registered with tg_bind_obs and it was the `obs` argument of the previous
+ * state-changing call on this env (tg_step / tg_reset / tg_primitive_step), only the rows of envs that ran or were
+ * reset are written -- one kernel launch.  Any other `obs` has every row written (a second launch). */
 int tg_step(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done,
             uint8_t *ran, uint16_t *avail, void *stream);
+
+/* Declares `obs` (DEV [N][obs_dim] f32) a persistent buffer of the caller that only this library writes: tg_step
+ * calls that pass it then update just the rows that changed (see tg_step).  NULL unbinds. */
+int tg_bind_obs(tg_env *env, float *obs);
 
 /* Same, with HOST buffers (pinned recommended): copies actions in, runs the step, copies
  * obs/reward/done(/ran) out and synchronises the stream.  Any output may be NULL. */
@@ -217,6 +225,11 @@ int tg_stats_clear(tg_env *env, void *stream);
  * writes %globaltimer (ns) at its phase boundaries: start, levels staged, option sort, classified, class sort,
  * options executed, outputs written, statistics done.  Used by tools/bench_phases.py; not part of the reference surface. */
 int tg_debug_phase_buffer(tg_env *env, uint64_t *stamps);
+
+/* Debug / tuning: environments per step-kernel CTA (32..4096, rounded up to a multiple of 4; 0 = automatic, the
+ * default, which also honours the TG_STEP_TILE environment variable read by tg_create).  Results never depend on it;
+ * the parity tests use it to run every tile-size-dependent code path against the oracle. */
+int tg_debug_set_step_tile(tg_env *env, int32_t tile);
 
 /* how many kernels this library has launched on behalf of `env` (bench bookkeeping) */
 int64_t tg_launch_count(const tg_env *env);

@@ -7,7 +7,7 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gym_treasure_game_b200 import VectorTreasureGame
 
-NAMES = ["start", "levels", "opt-sort", "classify", "cls-sort", "", "chunks", "stats"]
+NAMES = ["start", "levels", "phase-A", "sort", "t0-left-B", "phase-B", "stats", ""]
 
 
 def run(n, scenario, flush_mb=512, reps=7):
