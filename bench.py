@@ -5,11 +5,14 @@
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU algorithm
 
 Workload (BASELINE.json configs[2], the configuration the headline metric is quoted on):
-treasure_game-v0, vector-state observations, 1,048,576 environments per GPU, uniform-random
-option ids, 100-step time limit with auto-reset.  One "step" = one TreasureGame.step for every
-env of the batch (runnable or not).  N > 1: one process per GPU (torchrun), env ids sharded
-contiguously, no data-path collective; the episode-statistics vector is all-reduced with NCCL
-on a side stream every 100 steps and once at the end ("scaling": "weak").
+treasure_game-v0, vector-state observations, 1,048,576 environments in total, sharded contiguously
+over the N GPUs (N = 1: all of them on one GPU; "scaling": "strong"), uniform-random option ids,
+100-step time limit with auto-reset, in the steady state of that process: episode phases are
+desynchronised before anything is timed, so about 1 % of the envs hit the time limit in every
+step.  One "step" = one TreasureGame.step for every env of the batch (runnable or not).  N > 1: one
+process per GPU (torchrun), no data-path collective; the episode-statistics vector is all-reduced
+with NCCL on a side stream every 100 steps and once at the end.  The weak-scaling reading
+(1,048,576 envs per GPU) is timed next to it and reported under aux.
 
 Timing: CUDA events on the launching stream around every step kernel; between timed steps a
 512 MiB buffer is overwritten to flush the 126 MB L2 (outside the event pairs); the K steps are
@@ -29,11 +32,11 @@ sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_ENV_STEP = 125          # SURVEY.md 8(d); this layout moves 126 (52 read + 74 written)
 ALGO_BYTES_PER_FRAME = 1258024         # 624*672*3 written + 40 state bytes read
-ENVS_PER_GPU = 1 << 20
+TOTAL_ENVS = 1 << 20
 MAX_EPISODE_STEPS = 100
 METRIC, UNIT = "env_steps_per_s", "env-steps/s"
-WORKLOAD = ("treasure_game-v0 vector-state obs, 1,048,576 envs per GPU (BASELINE configs[2] shard), "
-            "uniform-random option ids, 100-step time limit + auto-reset")
+WORKLOAD = ("treasure_game-v0 vector-state obs, 1,048,576 envs in total sharded over the GPUs (BASELINE configs[2]), "
+            "uniform-random option ids, 100-step time limit + auto-reset, steady state (desynchronised episodes)")
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -206,7 +209,7 @@ def run_reference(args, rank):
     res["sample"] = "each step = " + res["sample"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "CPU arm: reference algorithm (pure-Python port; the Python "
                        "reference itself cannot travel to the GPU box), all host cores, README loop"},
             "cpu_baseline": res,
@@ -216,14 +219,82 @@ def run_reference(args, rank):
 
 
 # ----------------------------------------------------------------------------- main arm
+def timed_steps(torch, dist, env, dev, world, n, K, W, seed, stats_every=100):
+    """W untimed + K timed steps of one batch in steady state.  Returns per-step event times (ms), the max-over-ranks
+    total (s), launches, statistics (all ranks), clocks, wall time and draws per step."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    actions = torch.empty((n,), dtype=torch.int32, device=dev)
+
+    def new_actions():
+        # i.i.d. uniform option ids, regenerated on the device for every step (BASELINE configs[1]/[2]);
+        # a short cycled pool would make every env's action sequence periodic and shrink the work
+        return torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device=dev, out=actions)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    side = torch.cuda.Stream(device=dev)
+    stats_buf = torch.zeros(8, dtype=torch.int64, device=dev)
+
+    def stats_allreduce():
+        # the path's only collective: 64-byte int64[8] sum, off the critical path
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            stats_buf.copy_(env.stats_tensor())
+            if world > 1:
+                dist.all_reduce(stats_buf)
+
+    desynchronise(env, torch, new_actions)            # outside the timed region: steady state of the workload
+    for k in range(W):
+        env.step_raw(new_actions())
+    env.clear_stats()
+    draws0 = int(env.get_state()["misc"][:, 3].to(torch.int64).sum().item())     # work accounting, outside the timed region
+    barrier()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    launches0 = env.launch_count
+    t_wall0 = time.perf_counter()
+    for k in range(K):
+        new_actions()                                   # not timed: inputs are resident before the event pair
+        flush.zero_()                                   # L2 flush, outside the event pair
+        starts[k].record()
+        env.step_raw(actions)
+        ends[k].record()
+        if (k + 1) % stats_every == 0:
+            stats_allreduce()
+    stats_allreduce()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = env.launch_count - launches0
+    draws1 = int(env.get_state()["misc"][:, 3].to(torch.int64).sum().item())    # after the launch count was taken
+    clocks = sampler.finish()
+    per_step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = torch.tensor([sum(per_step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    stats = dict(zip(["episodes", "successes", "return_sum", "episode_steps_sum", "primitive_ticks",
+                      "runnable_steps", "gym_steps", "errors"], (int(v) for v in stats_buf.cpu())))
+    del flush
+    return dict(per_step_ms=per_step_ms, total_s=float(total_ms.item()) / 1000.0, launches=launches, stats=stats,
+                clocks=clocks, wall=t_wall, draws_per_step=(draws1 - draws0) / max(n * K, 1), new_actions=new_actions,
+                barrier=barrier)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
-    ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary configs (4096 envs, RGB render, CPU baselines)")
+    ap.add_argument("--total-envs", type=int, default=TOTAL_ENVS)
+    ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary configs (4096 envs, shards, RGB render, weak scaling, CPU baselines)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     if args.warmup < 3:
@@ -237,7 +308,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from gym_treasure_game_b200 import VectorTreasureGame
+    from gym_treasure_game_b200 import VectorTreasureGame, shard_range
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
@@ -245,74 +316,22 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n = args.envs_per_gpu
+    total = args.total_envs
+    lo, hi = shard_range(total, rank, world)            # strong scaling: BASELINE configs[2] shards 1,048,576 envs over the GPUs
+    n = hi - lo
     K, W = args.steps, args.warmup
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     env = VectorTreasureGame(n, device=dev, seed=0, max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True,
-                             first_env_id=rank * n, render=False)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    actions = torch.empty((n,), dtype=torch.int32, device=dev)
-
-    def new_actions():
-        # i.i.d. uniform option ids, regenerated on the device for every step (BASELINE configs[1]/[2]);
-        # a short cycled pool would make every env's action sequence periodic and shrink the work
-        return torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device=dev, out=actions)
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    side = torch.cuda.Stream(device=dev)
-    stats_buf = torch.zeros(8, dtype=torch.int64, device=dev)
-
-    def stats_allreduce():
-        # the path's only collective: 64-byte int64[8] sum, off the critical path
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            stats_buf.copy_(env.stats_tensor())
-            if world > 1:
-                dist.all_reduce(stats_buf)
-
-    for k in range(W):
-        env.step_raw(new_actions())
-    env.clear_stats()
-    draws0 = int(env.get_state()["misc"][:, 3].to(torch.int64).sum().item())     # work accounting, outside the timed region
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    launches0 = env.launch_count
-    t_wall0 = time.perf_counter()
-    for k in range(K):
-        new_actions()                                   # not timed: inputs are resident before the event pair
-        flush.zero_()                                   # L2 flush, outside the event pair
-        starts[k].record()
-        env.step_raw(actions)
-        ends[k].record()
-        if (k + 1) % 100 == 0:
-            stats_allreduce()
-    stats_allreduce()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = env.launch_count - launches0
-    draws1 = int(env.get_state()["misc"][:, 3].to(torch.int64).sum().item())    # after the launch count was taken
-    clocks = sampler.finish()
-    per_step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    total_ms = torch.tensor([sum(per_step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_s = float(total_ms.item()) / 1000.0
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    stats = dict(zip(["episodes", "successes", "return_sum", "episode_steps_sum", "primitive_ticks",
-                      "runnable_steps", "gym_steps", "errors"], (int(v) for v in stats_buf.cpu())))
-    value = world * n * K / total_s
+                             first_env_id=lo, render=False)
+    r = timed_steps(torch, dist, env, dev, world, n, K, W, seed=1234 + rank)
+    per_step_ms, total_s, stats, barrier, new_actions = r["per_step_ms"], r["total_s"], r["stats"], r["barrier"], r["new_actions"]
+    value = total * K / total_s
+    if stats["episodes"] <= 0:
+        raise SystemExit("bench.py: no episode ended inside the timed region -- the workload is not in its steady state")
 
     # ---- end-to-end through the C ABI with HOST buffers: H2D actions, step, D2H results, host arrays complete on return.
     # Headline: tg_step_host_sparse (only the rows of envs that ran or were reset cross the bus; the host arrays of the
-    # previous call are patched in place).  tg_step_host (everything crosses) is timed next to it.
+    # previous call are patched in place).  tg_step_host (everything crosses) is timed next to it under its own key.
     Ke = min(K, 20)
     host = env.make_host_buffers()
     hpool = [new_actions().cpu().pin_memory() for _ in range(Ke)]
@@ -323,51 +342,57 @@ def main():
             fn(host)
         barrier()
         h0, d0 = env.host_traffic()
+        ts = []
         t0 = time.perf_counter()
         for k in range(Ke):
             host["actions"] = hpool[k % len(hpool)]
+            t1 = time.perf_counter()
             fn(host)
+            ts.append(time.perf_counter() - t1)
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         h1, d1 = env.host_traffic()
-        return world * n * Ke / float(dt.item()), (h1 - h0) // Ke, (d1 - d0) // Ke
+        ts.sort()
+        return total * Ke / float(dt.item()), (h1 - h0) // Ke, (d1 - d0) // Ke, 1e3 * ts[len(ts) // 2], 1e3 * ts[-1]
 
-    dense_value, dense_h2d, dense_d2h = time_host(env.step_host)
-    sparse_value, sparse_h2d, sparse_d2h = time_host(env.step_host_sparse)
-    # both are public entry points with the same results; the line's e2e is the faster one on this box (the sparse
-    # path trades bus bytes for host-side patching, which several ranks sharing one host can lose), the other is kept
-    paths = {"tg_step_host_sparse": {"value": sparse_value, "h2d_bytes_per_step": sparse_h2d, "d2h_bytes_per_step": sparse_d2h,
-                                     "api": "tg_step_host_sparse (pinned host buffers; H2D actions, chunked step kernels that compact the envs whose outputs changed into records, D2H of the records, host threads patch obs/reward/done/ran in place; stream sync inside the call; bytes counted by the library per copy)"},
-             "tg_step_host": {"value": dense_value, "h2d_bytes_per_step": dense_h2d, "d2h_bytes_per_step": dense_d2h,
-                              "api": "tg_step_host (pinned host buffers; H2D actions, chunked step kernels overlapping the D2H of every env's obs/reward/done/ran; stream sync inside the call; bytes counted by the library per copy)"}}
-    best = max(paths, key=lambda k: paths[k]["value"])
-    other = [k for k in paths if k != best][0]
-    e2e_value, h2d, d2h = paths[best]["value"], paths[best]["h2d_bytes_per_step"], paths[best]["d2h_bytes_per_step"]
+    dense = time_host(env.step_host)
+    sparse = time_host(env.step_host_sparse)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1000.0 * total_s / K, "ms_per_step_median": sorted(per_step_ms)[K // 2], "ms_per_step_max": max(per_step_ms),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int32+f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": n, "total_envs": n * world, "max_episode_steps": MAX_EPISODE_STEPS,
+        "config": {"workload": WORKLOAD, "total_envs": total, "envs_per_gpu": n, "max_episode_steps": MAX_EPISODE_STEPS,
+                   "steady_state": "100 steps, episode ages redrawn uniformly in [0, 100), 110 more steps; then the W warm-up steps",
                    "l2": "512 MiB buffer overwritten between timed steps (outside the event pairs)",
-                   "actions": "torch.randint on the device before every step, outside the timed event pair", "collective": "NCCL all-reduce of int64[8] stats every 100 steps, side stream"},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                "api": paths[best]["api"], "other_path": dict(paths[other], name=other)},
-        "gpu_launches": launches,
+                   "actions": "torch.randint on the device before every step, outside the timed event pair",
+                   "collective": "NCCL all-reduce of int64[8] stats every 100 steps, side stream"},
+        "clocks": r["clocks"],
+        "e2e": {"value": sparse[0], "unit": UNIT, "h2d_bytes_per_step": sparse[1], "d2h_bytes_per_step": sparse[2], "steps": Ke,
+                "ms_per_step_median_rank0": sparse[3], "ms_per_step_max_rank0": sparse[4],
+                "api": "tg_step_host_sparse (pinned host buffers; H2D actions, chunked step kernels that compact the envs whose outputs "
+                       "changed into records, one D2H copy per chunk of header + records, host threads patch obs/reward/done/ran in "
+                       "place; stream sync inside the call; bytes counted by the library per copy)",
+                "dense_path": {"name": "tg_step_host", "value": dense[0], "h2d_bytes_per_step": dense[1], "d2h_bytes_per_step": dense[2],
+                               "ms_per_step_median_rank0": dense[3],
+                               "api": "tg_step_host (pinned host buffers; H2D actions, chunked step kernels overlapping the D2H of every "
+                                      "env's obs/reward/done/ran; stream sync inside the call)"}},
+        "gpu_launches": r["launches"],
         "roofline": {"bound": "hbm", "achieved": (n * ALGO_BYTES_PER_ENV_STEP) / (total_s / K) / 1e9,
                      "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
-                     "kernel": "tg_step_kernel<false,2,4096> (2364-env tiles, 444 CTAs)", "algorithmic_bytes_per_launch": n * ALGO_BYTES_PER_ENV_STEP,
-                     "note": "instruction-issue / serial-chain bound, not HBM bound (DESIGN.md 3.1); see work.primitive_ticks_per_s"},
+                     "kernel": "tg_step_kernel<false,2> (%d envs per launch, automatic tile size)" % n,
+                     "algorithmic_bytes_per_launch": n * ALGO_BYTES_PER_ENV_STEP,
+                     "note": "per GPU; serial-chain / instruction-fetch bound, not HBM bound (DESIGN.md 3.1); see work.primitive_ticks_per_s"},
         "work": {"runnable_fraction": stats["runnable_steps"] / max(stats["gym_steps"], 1),
                  "primitive_ticks_per_step": stats["primitive_ticks"] / max(stats["gym_steps"], 1),
                  "primitive_ticks_per_s": stats["primitive_ticks"] / total_s if stats["gym_steps"] else None,
-                 "rng_draws_per_step_rank0": (draws1 - draws0) / max(n * K, 1),
+                 "episodes_per_step_fraction": stats["episodes"] / max(stats["gym_steps"], 1),
+                 "rng_draws_per_step_rank0": r["draws_per_step"],
                  "stats_all_ranks": stats},
-        "wall_s_timed_region_incl_flush": t_wall,
+        "wall_s_timed_region_incl_flush": r["wall"],
     }
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -379,17 +404,32 @@ def main():
     line["roofline"]["peak"] = peak
     line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
     traffic_path = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
-    if os.path.exists(traffic_path):
+    if os.path.exists(traffic_path) and n == TOTAL_ENVS:
         line["roofline"]["traffic"] = json.load(open(traffic_path)).get("dram_bytes_per_launch")
 
     env.close()
-    del env
+    del env, host, hpool
     torch.cuda.empty_cache()
 
-    if rank == 0 and world == 1 and not args.no_aux:
-        line["aux"] = aux_configs(torch, dev, peak)
-        line["cpu_baseline"] = cpu_baseline_python(args.cpu_seconds)
-        line["cpu_baseline_c"] = cpu_baseline_c(min(args.cpu_seconds, 6.0))
+    if not args.no_aux:
+        aux = {}
+        if world > 1:
+            # the weak-scaling reading of configs[2]: 1,048,576 envs per GPU, same steady state, 20 timed steps
+            wn = TOTAL_ENVS
+            wenv = VectorTreasureGame(wn, device=dev, seed=0, max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True,
+                                      first_env_id=rank * wn, render=False)
+            wr = timed_steps(torch, dist, wenv, dev, world, wn, 20, 5, seed=99 + rank)
+            aux["weak_1048576_envs_per_gpu"] = {"env_steps_per_s": world * wn * 20 / wr["total_s"], "ms_per_step": 1000.0 * wr["total_s"] / 20,
+                                                "scaling": "weak", "total_envs": world * wn}
+            wenv.close()
+            del wenv
+            torch.cuda.empty_cache()
+        if rank == 0 and world == 1:
+            aux.update(aux_configs(torch, dev, peak))
+            line["cpu_baseline"] = cpu_baseline_python(args.cpu_seconds)
+            line["cpu_baseline_c"] = cpu_baseline_c(min(args.cpu_seconds, 6.0))
+        if aux:
+            line["aux"] = aux
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -398,7 +438,8 @@ def main():
 
 
 def aux_configs(torch, dev, peak):
-    """BASELINE configs[1] (4096 envs) and configs[3] (16384 envs, RGB render) on one GPU."""
+    """One GPU: BASELINE configs[1] (4096 envs), the per-GPU shards of configs[2] at 2 / 4 / 8 GPUs, and configs[3]
+    (16384 envs, RGB render).  Every batch is brought to the same steady state as the main line first."""
     from gym_treasure_game_b200 import VectorTreasureGame
     out = {}
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
@@ -417,48 +458,44 @@ def aux_configs(torch, dev, peak):
             tot += s.elapsed_time(e)
         return tot / iters / 1000.0
 
-    # configs[1]: 4096 envs
-    n = 4096
-    env = VectorTreasureGame(n, device=dev, seed=0, max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True, render=False)
-    pool = [torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device=dev) for _ in range(512)]
-    it = [0]
+    def steady(n, render=False):
+        env = VectorTreasureGame(n, device=dev, seed=0, max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True, render=render)
+        acts = torch.empty((n,), dtype=torch.int32, device=dev)
+        new_actions = lambda: torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device=dev, out=acts)   # fresh i.i.d. ids every step
+        desynchronise(env, torch, new_actions)
+        return env, acts, new_actions
 
-    def step4096():
-        env.step_raw(pool[it[0] % 512]); it[0] += 1        # 512 distinct i.i.d. batches: no periodicity within a run
-    for _ in range(100):
-        step4096()
-    t = timed(step4096, 300)
-    out["cfg2_4096_envs"] = {"env_steps_per_s": n / t, "ms_per_step": t * 1e3,
-                             "roofline_frac": n * ALGO_BYTES_PER_ENV_STEP / t / 1e9 / peak}
-    env.close()
+    for name, n, iters in (("cfg2_4096_envs", 4096, 300), ("cfg3_shard_131072_envs", 131072, 200),
+                           ("cfg3_shard_262144_envs", 262144, 100), ("cfg3_shard_524288_envs", 524288, 100)):
+        env, acts, new_actions = steady(n)
 
-    # configs[2] read as strong scaling: 1,048,576 envs over 8 GPUs = 131,072 envs per GPU (the main line above is the
-    # weak-scaling reading, 1,048,576 envs per GPU)
-    n = 131072
-    env = VectorTreasureGame(n, device=dev, seed=0, max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True, render=False)
-    pool = [torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device=dev) for _ in range(64)]
-
-    def step131k():
-        env.step_raw(pool[it[0] % 64]); it[0] += 1
-    for _ in range(100):
-        step131k()
-    t = timed(step131k, 200)
-    out["cfg3_strong_shard_131072_envs"] = {"env_steps_per_s": n / t, "ms_per_step": t * 1e3,
-                                            "roofline_frac": n * ALGO_BYTES_PER_ENV_STEP / t / 1e9 / peak,
-                                            "note": "one GPU's shard when 1,048,576 envs are split over 8 GPUs"}
-    env.close()
+        def step():
+            env.step_raw(acts)
+        # the action refresh stays outside the event pair, as in the main line
+        for _ in range(5):
+            new_actions(); step()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(iters):
+            new_actions(); flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); step(); e.record()
+            e.synchronize()
+            tot += s.elapsed_time(e)
+        t = tot / iters / 1000.0
+        out[name] = {"env_steps_per_s": n / t, "ms_per_step": t * 1e3, "roofline_frac": n * ALGO_BYTES_PER_ENV_STEP / t / 1e9 / peak}
+        if n > 4096:
+            out[name]["note"] = "one GPU's shard when 1,048,576 envs are split over %d GPUs" % (TOTAL_ENVS // n)
+        env.close()
 
     # configs[3]: 16384 envs, RGB observations
     n = 16384
-    env = VectorTreasureGame(n, device=dev, seed=0, max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True, render=True)
-    pool = [torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device=dev) for _ in range(64)]
+    env, acts, new_actions = steady(n, render=True)
     frames = torch.empty((n, 624, 672, 3), dtype=torch.uint8, device=dev)
-    for k in range(40):
-        env.step_raw(pool[k % 64])
     t_r = timed(lambda: env.render(out=frames), 10, warm=3)
 
     def step_render():
-        env.step_raw(pool[it[0] % 64]); it[0] += 1
+        new_actions(); env.step_raw(acts)
         env.render(out=frames)
     t_sr = timed(step_render, 10, warm=3)
     out["cfg4_render_16384_envs"] = {

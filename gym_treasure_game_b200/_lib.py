@@ -60,10 +60,12 @@ _SIGNATURES = {
     "tg_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tg_step": (C.c_int, [C.c_void_p] * 8),
     "tg_bind_obs": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tg_bind_flags": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tg_step_host": (C.c_int, [C.c_void_p] * 7),
     "tg_step_host_sparse": (C.c_int, [C.c_void_p] * 7),
     "tg_available_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tg_render": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "tg_step_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 7),
     "tg_blend": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "tg_background": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "tg_blit_alpha": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

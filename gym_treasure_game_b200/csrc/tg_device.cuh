@@ -373,20 +373,23 @@ __device__ __forceinline__ void drop_key(Env<NI> &e, const LevelBlob &L) {
     }
 }
 
-// impl:321-329
+// impl:321-329.  One call site of set_val for both kinds of object (the trigger walk is the bulk of this code).
 template <bool TAPE, int NI>
 __device__ __forceinline__ void interact(Env<NI> &e, const LevelBlob &L) {
     for (int o = 0; o < L.n_objs; o++) {
-        int k = L.obj_kind[o], i = L.obj_idx[o];
+        const int k = L.obj_kind[o], i = L.obj_idx[o];
+        bool set = false, val = false, drop = false;
         if (k == TG_HANDLE) {
             if (!near_px(e.px, e.py, L.handle_cx[i] * S, L.handle_cy[i] * S, 36 * 36)) continue;   // objs:115
-            bool up = (e.flags >> (F_HANDLES + i)) & 1u;
-            if (draw_k<TAPE>(e) <= 7205759403792794ull) set_val<TAPE>(e, L, o, !up);   // objs:117-122: uniform(0,1) <= 0.8  (0.8 * 2^53)
+            const bool up = (e.flags >> (F_HANDLES + i)) & 1u;
+            if (draw_k<TAPE>(e) <= 7205759403792794ull) { set = true; val = !up; }   // objs:117-122: uniform(0,1) <= 0.8  (0.8 * 2^53)
             else e.angles[(int64_t)i * e.n] = handle_angle(up, draw<TAPE>(e));
         } else if (k == TG_BOLT) {
             if (!near_px(e.px, e.py, L.bolt_cx[i] * S, L.bolt_cy[i] * S, 24 * 24)) continue;
-            if (has_key(L, e.flags)) { set_val<TAPE>(e, L, o, false); drop_key(e, L); }          // impl:326-329
+            if (has_key(L, e.flags)) { set = true; val = false; drop = true; }                    // impl:326-329
         }
+        if (set) set_val<TAPE>(e, L, o, val);
+        if (drop) drop_key(e, L);
     }
 }
 
@@ -747,6 +750,45 @@ __device__ __forceinline__ bool fall_to_rest(Env<NI> &e, const LevelBlob &L, int
     return true;
 }
 
+// The option loop in its general form (opt:20-36 with the policies of opts:74-85, 146-157, 168-173, 184-189, 231-244,
+// 297-314, 367-384, 426-439, 457-460): policy step, primitive tick (impl:290-359), until the policy says done -- whose
+// action is still executed.  Complete for every option; run_option_to_end enters it with whatever its straight-line
+// loops left.  FAST allows the closed-form fall at the end of drops and jumps; `after_tick(n)` runs after every
+// primitive tick (the per-tick frame streaming of tg_step_frames, opt:33-34, runs it with FAST = false from n = 0).
+template <bool TAPE, int NI, bool INTERACT_OK, bool FAST, class F>
+__device__ __forceinline__ void general_option_loop(Env<NI> &e, const LevelBlob &L, int k, int s, int tpx, int &n, F after_tick) {
+    bool done = false;
+    do {
+        int act, lad = -1;
+        const bool al = abs(tpx - e.px) < 4;              // close_enough_*  (opts:69-72 ...)
+        if (k <= TG_GO_RIGHT) {                           // opts:74-85 / 146-157
+            done = al; act = (s < 0) ? A_LEFT : A_RIGHT;
+        } else if (k == TG_UP_LADDER) {                   // opts:168-173
+            done = !ladder_probe(L, e.px, e.py, true); act = done ? A_NOP : A_UP; lad = 1;
+        } else if (k == TG_DOWN_LADDER) {                 // opts:184-189
+            done = !ladder_probe(L, e.px, e.py, false); act = done ? A_NOP : A_DOWN; lad = 1;
+        } else if (k == TG_INTERACT) {                    // opts:457-460
+            done = true; act = A_INTERACT;
+        } else if (k <= TG_DOWN_RIGHT) {                  // opts:231-244 / 426-439
+            if (al) { if (FAST && fall_to_rest(e, L, n)) break; done = !can_fall_m(e, L); act = A_NOP; }
+            else act = (s < 0) ? A_LEFT : A_RIGHT;
+        } else {                                          // opts:297-314 / 367-384
+            if (n == 0) act = A_JUMP;
+            else if (al) { if (FAST && fall_to_rest(e, L, n)) break; done = !can_fall_m(e, L); act = A_NOP; }
+            else {
+                bool blocked = !side_free_m(e, L, e.px + 16 * s);
+                bool grounded = !can_fall_m(e, L);
+                bool rev = grounded && blocked;
+                act = ((s < 0) != rev) ? A_LEFT : A_RIGHT;
+            }
+        }
+        tick<TAPE, NI, INTERACT_OK>(e, L, act, lad);
+        n++;
+        after_tick(n);
+        if (n >= TG_TICK_CAP && !done) { e.flags |= 1u << F_ERROR; break; }
+    } while (!done);
+}
+
 // Runs option k (already known to be runnable, target column tcx from option_setup) to termination.  Returns the
 // number of primitive ticks; reward = -ticks - 4*[jump option] (impl:15-16,356-359).  `valid` = this lane has an env
 // and an option to run (every lane of a warp may call it).
@@ -899,36 +941,7 @@ __device__ __forceinline__ int run_option_to_end(Env<NI> &e, const LevelBlob &L,
         if (!move_until_aligned<TAPE>(e, L, k >= TG_JUMP_LEFT, s, tpx, n)) { e.flags |= 1u << F_ERROR; done = true; }
     }
     // ---- everything else, and what the loops above left: policy step + general tick, one lane at its own pace ----
-    if (valid && !done) {
-        do {
-            int act, lad = -1;
-            const bool al = abs(tpx - e.px) < 4;              // close_enough_*  (opts:69-72 ...)
-            if (k <= TG_GO_RIGHT) {                           // opts:74-85 / 146-157
-                done = al; act = (s < 0) ? A_LEFT : A_RIGHT;
-            } else if (k == TG_UP_LADDER) {                   // opts:168-173
-                done = !ladder_probe(L, e.px, e.py, true); act = done ? A_NOP : A_UP; lad = 1;
-            } else if (k == TG_DOWN_LADDER) {                 // opts:184-189
-                done = !ladder_probe(L, e.px, e.py, false); act = done ? A_NOP : A_DOWN; lad = 1;
-            } else if (k == TG_INTERACT) {                    // opts:457-460
-                done = true; act = A_INTERACT;
-            } else if (k <= TG_DOWN_RIGHT) {                  // opts:231-244 / 426-439
-                if (al) { if (fall_to_rest(e, L, n)) { done = true; break; } done = !can_fall_m(e, L); act = A_NOP; }
-                else act = (s < 0) ? A_LEFT : A_RIGHT;
-            } else {                                          // opts:297-314 / 367-384
-                if (n == 0) act = A_JUMP;
-                else if (al) { if (fall_to_rest(e, L, n)) { done = true; break; } done = !can_fall_m(e, L); act = A_NOP; }
-                else {
-                    bool blocked = !side_free_m(e, L, e.px + 16 * s);
-                    bool grounded = !can_fall_m(e, L);
-                    bool rev = grounded && blocked;
-                    act = ((s < 0) != rev) ? A_LEFT : A_RIGHT;
-                }
-            }
-            tick<TAPE, NI, INTERACT_OK>(e, L, act, lad);
-            n++;
-            if (n >= TG_TICK_CAP && !done) { e.flags |= 1u << F_ERROR; break; }
-        } while (!done);
-    }
+    if (valid && !done) general_option_loop<TAPE, NI, INTERACT_OK, true>(e, L, k, s, tpx, n, [](int) {});
     return n;
 }
 

@@ -43,6 +43,9 @@ cudaError_t launch_primitive(const BatchView &B, int ni, const int32_t *actions,
 cudaError_t launch_init_with_state(const BatchView &B, int ni, const double *states, const uint8_t *mask, cudaStream_t s);
 // observation rows of the envs [r_begin, r_begin + r_count) from their stored state
 cudaError_t launch_obs(const BatchView &B, int ni, float *obs, cudaStream_t s);
+// tg_step_frames: the M selected envs take one gym step tick by tick; per-tick states go to the snapshot batch S (M * T slots)
+cudaError_t launch_trace(const BatchView &B, const BatchView &S, int ni, const int64_t *env_ids, int M, const int32_t *actions, int T,
+                         int32_t *n_ticks, float *obs, float *rew, uint8_t *done, uint8_t *ran, cudaStream_t s);
 cudaError_t launch_mask(const BatchView &B, int ni, uint8_t *mask, cudaStream_t s);
 cudaError_t launch_get_state(const BatchView &B, const tg_state_view &v, cudaStream_t s);
 cudaError_t launch_set_state(const BatchView &B, const tg_state_view &v, cudaStream_t s);

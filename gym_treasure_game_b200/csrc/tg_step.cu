@@ -228,6 +228,18 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, int cap, const int
                     }
                 }
             }
+            if (B.flag_done) {                                         // bound flag views (cudaMalloc'ed by the caller's framework: 4-byte aligned rows of 4)
+                if (m == 4 && ((base & 3) == 0)) {
+                    *reinterpret_cast<uint32_t *>(B.flag_done + i0) = (dn | (dn >> 1)) & 0x01010101u;
+                    *reinterpret_cast<uint32_t *>(B.flag_term + i0) = dn & 0x01010101u;
+                    *reinterpret_cast<uint32_t *>(B.flag_trunc + i0) = (dn >> 1) & 0x01010101u;
+                } else {
+                    for (int u = 0; u < m; u++) {
+                        const uint32_t d1 = (dn >> (8 * u)) & 255u;
+                        B.flag_done[i0 + u] = d1 ? 1 : 0; B.flag_term[i0 + u] = d1 & 1u; B.flag_trunc[i0 + u] = (d1 >> 1) & 1u;
+                    }
+                }
+            }
             if (vo && m == 4) {
                 if (reward) *reinterpret_cast<float4 *>(reward + i0) = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (done_out) *reinterpret_cast<uint32_t *>(done_out + i0) = dn;
@@ -351,6 +363,7 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, int cap, const int
         if (reward) reward[i] = (float)r;
         if (done_out) done_out[i] = (uint8_t)d;
         if (ran_out) ran_out[i] = (uint8_t)1;
+        if (B.flag_done) { B.flag_done[i] = d ? 1 : 0; B.flag_term[i] = d & 1u; B.flag_trunc[i] = (d >> 1) & 1u; }
         if (B.phase_ts && lane == 0 && q < 128) {                                 // [grid][8] phase stamps, then [grid][128][4] chunks
             unsigned long long t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1) :: "memory");
@@ -524,6 +537,78 @@ tg_primitive_kernel(BatchView B, const int32_t *__restrict__ actions, float *__r
     }
     stats_accumulate(sh_stats, B.stats, st);
     finish_launch(B);
+}
+
+// tg_step_frames: the option layer with a drawer (opt:20-36 with opt:33-34: draw_domain() after every primitive tick).
+// The M selected envs take one gym step; their option runs tick by tick in the general loop (no multi-tick shortcuts) and
+// after tick t the env's state is copied to slot [k][t-1] of the snapshot arrays S (core / items / angles / level id, laid
+// out like a batch of M * T envs), which the renderer then draws.  Slots after the option's last tick repeat the final
+// state of the option (before any auto-reset).  Accounting as in tg_step_kernel; the batch-wide step counter does not move
+// (only these envs stepped), so their episode start is moved back by one instead.
+template <bool TAPE, int NI>
+__global__ void __launch_bounds__(AUX_THREADS)
+tg_trace_kernel(BatchView B, BatchView SN, const int64_t *__restrict__ env_ids, int M, const int32_t *__restrict__ actions, int T,
+                int32_t *__restrict__ n_ticks, float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done_out,
+                uint8_t *__restrict__ ran_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LevelBlob *levels = reinterpret_cast<LevelBlob *>(smem_raw);
+    __shared__ uint64_t bar;
+    stage_levels(levels, B.levels, B.n_levels, &bar);
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= M) return;
+    const int64_t i = env_ids[k];
+    if (i < 0 || i >= B.n) { n_ticks[k] = -1; return; }
+    const int lid = B.level_id ? B.level_id[i] : 0;
+    const LevelBlob &L = levels[lid];
+    const uint32_t t_now = B.step_counter[0];
+    Env<NI> e;
+    uint4 acct;
+    load_env(e, B, i, acct);
+    auto snap = [&](int slot) {
+        const int64_t q = (int64_t)k * T + slot;
+        uint4 c;
+        c.x = pack_player(e.px, e.py, e.sticky); c.y = e.flags; c.z = pack_xy(e.ix[0], e.iy[0]);
+        c.w = (NI > 1) ? pack_xy(e.ix[NI > 1 ? 1 : 0], e.iy[NI > 1 ? 1 : 0]) : 0u;
+        SN.core[q] = c;
+        if (NI > 2 && SN.items23) SN.items23[q] = make_uint2(pack_xy(e.ix[NI > 2 ? 2 : 0], e.iy[NI > 2 ? 2 : 0]), NI > 3 ? pack_xy(e.ix[NI > 3 ? 3 : 0], e.iy[NI > 3 ? 3 : 0]) : 0u);
+        for (int h = 0; h < TG_MAX_HANDLES; h++) SN.angles[(int64_t)h * SN.n + q] = B.angles[(int64_t)h * B.n + i];
+        if (SN.level_id) const_cast<uint8_t *>(SN.level_id)[q] = (uint8_t)lid;
+    };
+    const int a = actions[k];
+    int tcx = 0; bool err = false;
+    const bool runnable = (unsigned)a < (unsigned)TG_NUM_OPTIONS && option_setup(e, L, a, tcx, err);
+    const uint32_t err0 = e.flags & (1u << F_ERROR);
+    if (err) e.flags |= 1u << F_ERROR;
+    int n = 0;
+    if (runnable) {
+        const int s = (a == TG_GO_LEFT || a == TG_DOWN_LEFT || a == TG_JUMP_LEFT) ? -1 : 1;
+        general_option_loop<TAPE, NI, true, false>(e, L, a, s, tcx * S + S / 2, n, [&](int t) { if (t <= T) snap(t - 1); });
+    }
+    for (int t = min(n, T); t < T; t++) snap(t);
+    n_ticks[k] = n;
+    const int r = runnable ? -n - ((a >= TG_JUMP_LEFT) ? 4 : 0) : 0;
+    acct.y = (uint32_t)((int)acct.y + r);
+    const uint32_t steps = t_now + 1u - B.ep_start[i];
+    const bool term = is_done(e, L), trunc = B.max_steps > 0 && steps >= (uint32_t)B.max_steps;
+    const uint32_t d = (term ? TG_DONE_TERMINATED : 0) | (trunc ? TG_DONE_TRUNCATED : 0);
+    atomicAdd(&B.stats[ST_STEPS], 1ull);
+    if (runnable) { atomicAdd(&B.stats[ST_RAN], 1ull); atomicAdd(&B.stats[ST_TICKS], (unsigned long long)n); }
+    if ((e.flags & (1u << F_ERROR)) && !err0) atomicAdd(&B.stats[ST_ERRORS], 1ull);
+    uint32_t ep0 = B.ep_start[i] - 1u;                                           // one more gym step than the batch counter says
+    if (d) {
+        atomicAdd(&B.stats[ST_EPISODES], 1ull);
+        if (term) atomicAdd(&B.stats[ST_SUCCESS], 1ull);
+        atomicAdd(&B.stats[ST_RETURN], (unsigned long long)(long long)(int)acct.y);
+        atomicAdd(&B.stats[ST_EPSTEPS], (unsigned long long)steps);
+        if (B.auto_reset) { reset_env<TAPE>(e, L); acct.y = 0; ep0 = t_now; }
+    }
+    store_env(e, B, i, acct);
+    B.plan[i] = plan_of(e, L);
+    B.ep_start[i] = ep0;
+    if (obs) write_obs(e, L, B.obs_lut + (size_t)lid * 2 * OBS_LUT_N, obs + (int64_t)k * B.obs_dim, B.obs_dim);
+    if (reward) reward[k] = (float)r;
+    if (done_out) done_out[k] = (uint8_t)d;
+    if (ran_out) ran_out[k] = runnable ? 1 : 0;
 }
 
 template <bool TAPE, int NI>
@@ -713,6 +798,21 @@ cudaError_t launch_init_with_state(const BatchView &B, int ni, const double *sta
     } else {
         if (tape) tg_init_with_state_kernel<true, 4><<<g, AUX_THREADS, sm, s>>>(B, states, mask);
         else tg_init_with_state_kernel<false, 4><<<g, AUX_THREADS, sm, s>>>(B, states, mask);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace(const BatchView &B, const BatchView &S, int ni, const int64_t *env_ids, int M, const int32_t *actions, int T,
+                         int32_t *n_ticks, float *obs, float *rew, uint8_t *done, uint8_t *ran, cudaStream_t s) {
+    const unsigned g = grid_for(M, AUX_THREADS);
+    const size_t sm = level_smem(B);
+    const bool tape = B.tape != nullptr;
+    if (ni <= 2) {
+        if (tape) tg_trace_kernel<true, 2><<<g, AUX_THREADS, sm, s>>>(B, S, env_ids, M, actions, T, n_ticks, obs, rew, done, ran);
+        else tg_trace_kernel<false, 2><<<g, AUX_THREADS, sm, s>>>(B, S, env_ids, M, actions, T, n_ticks, obs, rew, done, ran);
+    } else {
+        if (tape) tg_trace_kernel<true, 4><<<g, AUX_THREADS, sm, s>>>(B, S, env_ids, M, actions, T, n_ticks, obs, rew, done, ran);
+        else tg_trace_kernel<false, 4><<<g, AUX_THREADS, sm, s>>>(B, S, env_ids, M, actions, T, n_ticks, obs, rew, done, ran);
     }
     return cudaGetLastError();
 }

@@ -120,6 +120,9 @@ struct BatchView {
     uint32_t *sp_count;
     uint32_t *sp_recs;
     int32_t sp_words;
+    // optional 0 / 1 byte views of the step's done bits (tg_bind_flags): done != 0, terminated, truncated -- what a Gym-style
+    // caller wants as bool tensors, written by the step kernel itself instead of three elementwise launches afterwards
+    uint8_t *flag_done, *flag_term, *flag_trunc;
     unsigned long long *phase_ts; // debug: [grid][8] globaltimer stamps of the step kernel's phases, or NULL
 };
 

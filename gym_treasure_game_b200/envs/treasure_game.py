@@ -6,11 +6,13 @@ one-env ``VectorTreasureGame`` (there is no CPU implementation).
 """
 from __future__ import annotations
 
+import ctypes as C
 import random
 
 import numpy as np
 import torch
 
+from .. import _lib
 from ..level import BOLT, GOLD, HANDLE, KEY, Level
 from ..spaces import Box, Discrete
 from ..vector_env import OPTION_NAMES, VectorTreasureGame
@@ -61,12 +63,30 @@ class TreasureGame(_EnvBase):
         self.observation_space = Box(np.float32(0.0), np.float32(1.0), shape=(self.level.obs_dim,))   # :75
         self.viewer = None
         self.drawer = None                                        # created by the first render(), treasure_game.py:99-100
-        self._actions = torch.zeros(1, dtype=torch.int32, device=self._vec.device)
+        # One env: every input and output of a step lives in pinned host memory that the kernels read and write
+        # directly (unified addressing), so a step is two launches (tg_step, tg_get_state) and one stream
+        # synchronisation -- no torch kernels, no copies.
+        pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
+        self._act = pin((4,), torch.int32)
+        self._obs = pin((self._vec.obs_dim,), torch.float32)
+        self._rew, self._done, self._ran = pin((4,), torch.float32), pin((4,), torch.uint8), pin((4,), torch.uint8)
+        self._st = dict(pos=pin((1, 2), torch.int32), misc=pin((1, 4), torch.int32), doors=pin((1, _lib.MAX_DOORS), torch.uint8),
+                        handles=pin((1, _lib.MAX_HANDLES), torch.uint8), bolts=pin((1, _lib.MAX_BOLTS), torch.uint8),
+                        angles=pin((1, _lib.MAX_HANDLES), torch.float64), items=pin((1, _lib.MAX_ITEMS, 2), torch.int32),
+                        bag=pin((1, _lib.MAX_ITEMS), torch.int32), acct=pin((1, 3), torch.int64))
+        self._st_view = _lib.TgStateView(**{k: v.data_ptr() for k, v in self._st.items()})
+        self._L = self._vec._L
+        _lib.check(self._L.tg_bind_obs(self._vec._h, C.c_void_p(self._obs.data_ptr())))
 
     # -- helpers ---------------------------------------------------------------
+    def _sync_state(self):
+        """tg_get_state into the pinned buffers, then wait for the stream: the host sees the step's results."""
+        _lib.check(self._L.tg_get_state(self._vec._h, C.byref(self._st_view), self._vec._stream()))
+        torch.cuda.current_stream(self._vec.device).synchronize()
+
     def _state_vector(self):
-        """float64 state vector exactly as impl:368-378 builds it (python list)."""
-        s = self._vec.get_state()
+        """float64 state vector exactly as impl:368-378 builds it (python list), from the pinned state buffers."""
+        s = self._st
         H, W = self.level.frame_size
         pos = s["pos"][0].tolist()
         angles = s["angles"][0].tolist()
@@ -85,6 +105,7 @@ class TreasureGame(_EnvBase):
 
     # -- save / restore (the reference keeps these on ``env._env``: impl:368-400, 447-481) -------
     def get_state(self):
+        self._sync_state()
         return self._state_vector()
 
     def get_state_descriptors(self):
@@ -95,7 +116,8 @@ class TreasureGame(_EnvBase):
 
     # -- gym API ------------------------------------------------------------------
     def reset(self):
-        self._vec.reset()
+        _lib.check(self._L.tg_reset(self._vec._h, None, C.c_void_p(self._obs.data_ptr()), self._vec._stream()))
+        self._sync_state()
         return self._state_vector()
 
     @property
@@ -104,11 +126,14 @@ class TreasureGame(_EnvBase):
 
     def step(self, action):
         action = range(len(OPTION_NAMES))[action]     # IndexError on a bad id, like option_list[action] (:92)
-        self._actions[0] = action
-        _, reward, done, info = self._vec.step(self._actions)
-        ran = bool(info["ran"][0])
-        r = int(reward[0]) if ran else None           # option.run() returns None when it cannot run (_option.py:22-23)
-        return self._state_vector(), r, bool(info["terminated"][0]), {}
+        self._act[0] = action                         # pinned host memory: read by the kernel in place
+        _lib.check(self._L.tg_step(self._vec._h, C.c_void_p(self._act.data_ptr()), C.c_void_p(self._obs.data_ptr()),
+                                   C.c_void_p(self._rew.data_ptr()), C.c_void_p(self._done.data_ptr()),
+                                   C.c_void_p(self._ran.data_ptr()), None, self._vec._stream()))
+        self._sync_state()
+        ran = bool(self._ran[0])
+        r = int(self._rew[0]) if ran else None        # option.run() returns None when it cannot run (_option.py:22-23)
+        return self._state_vector(), r, bool(int(self._done[0]) & _lib.DONE_TERMINATED), {}
 
     def render(self, mode="human"):
         if self.drawer is None:

@@ -108,6 +108,7 @@ class VectorTreasureGame:
         self._done = torch.empty((n,), dtype=torch.uint8, device=d)
         self._ran = torch.empty((n,), dtype=torch.uint8, device=d)
         self._avail = None
+        self._flags = None
         self._mask = None
         self._stats = torch.zeros((8,), dtype=torch.int64, device=d)
         # the observation buffer lives as long as this object and only the library writes it: steps update just the
@@ -150,11 +151,16 @@ class VectorTreasureGame:
             raise ValueError("actions must have shape (%d,)" % self.num_envs)
         if want_available and self._avail is None:
             self._avail = torch.empty((self.num_envs,), dtype=torch.int16, device=self.device)
+        if self._flags is None:
+            # 0 / 1 byte arrays the step kernel fills itself (tg_bind_flags), handed out as bool views: one launch per step()
+            self._flags = tuple(torch.zeros((self.num_envs,), dtype=torch.uint8, device=self.device) for _ in range(3))
+            check(self._L.tg_bind_flags(self._h, _ptr(self._flags[0]), _ptr(self._flags[1]), _ptr(self._flags[2])))
+            self._flag_views = tuple(f.view(torch.bool) for f in self._flags)
+            self._ran_bool = self._ran.view(torch.bool)
         check(self._L.tg_step(self._h, _ptr(actions), _ptr(self._obs), _ptr(self._reward), _ptr(self._done),
                               _ptr(self._ran), _ptr(self._avail) if want_available else None, self._stream()))
-        done = self._done != 0
-        info = {"ran": self._ran.bool(), "terminated": (self._done & _lib.DONE_TERMINATED) != 0,
-                "truncated": (self._done & _lib.DONE_TRUNCATED) != 0}
+        done, terminated, truncated = self._flag_views
+        info = {"ran": self._ran_bool, "terminated": terminated, "truncated": truncated}
         if want_available:
             info["available"] = self._avail
         return self._obs, self._reward, done, info
@@ -179,6 +185,31 @@ class VectorTreasureGame:
         check(self._L.tg_primitive_step(self._h, _ptr(actions), _ptr(self._obs), _ptr(self._reward), _ptr(self._done),
                                         self._stream()))
         return self._obs, self._reward, self._done
+
+    def step_frames(self, env_ids, actions, max_ticks: int = 128, out: Optional[torch.Tensor] = None):
+        """The option layer with a drawer (``_option.py:20-36``, ``drawer.draw_domain()`` after every primitive tick):
+        the envs ``env_ids`` (distinct) take one gym step with ``actions``, and the frame after tick ``t`` of env ``k``
+        is ``frames[k, t-1]``; frames after the last tick repeat the final one.  Returns ``(frames (M, max_ticks, H, W,
+        3) uint8, n_ticks (M,) int32, obs (M, obs_dim), reward (M,), done_bits (M,), ran (M,))``; the other envs are
+        not stepped."""
+        ids = torch.as_tensor(env_ids, dtype=torch.int64).to(self.device).contiguous()
+        acts = torch.as_tensor(actions, dtype=torch.int32).to(self.device).contiguous()
+        m = int(ids.numel())
+        if acts.numel() != m or m < 1:
+            raise ValueError("one action per env id")
+        shape = (m, int(max_ticks)) + self.frame_shape
+        if out is None:
+            out = torch.empty(shape, dtype=torch.uint8, device=self.device)
+        elif tuple(out.shape) != shape or out.dtype != torch.uint8 or out.device != self.device or not out.is_contiguous() or out.data_ptr() % 16:
+            raise ValueError("out must be a contiguous, 16-byte aligned uint8 tensor of shape %s on %s" % (shape, self.device))
+        n_ticks = torch.empty((m,), dtype=torch.int32, device=self.device)
+        obs = torch.empty((m, self.obs_dim), dtype=torch.float32, device=self.device)
+        rew = torch.empty((m,), dtype=torch.float32, device=self.device)
+        done = torch.empty((m,), dtype=torch.uint8, device=self.device)
+        ran = torch.empty((m,), dtype=torch.uint8, device=self.device)
+        check(self._L.tg_step_frames(self._h, _ptr(ids), m, _ptr(acts), int(max_ticks), _ptr(out), _ptr(n_ticks), _ptr(obs),
+                                     _ptr(rew), _ptr(done), _ptr(ran), self._stream()))
+        return out, n_ticks, obs, rew, done, ran
 
     def make_host_buffers(self):
         """Pinned host buffers for ``step_host`` (actions in; obs, reward, done, ran out)."""

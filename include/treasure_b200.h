@@ -154,6 +154,12 @@ int tg_step(tg_env *env, const int32_t *actions, float *obs, float *reward, uint
  * calls that pass it then update just the rows that changed (see tg_step).  NULL unbinds. */
 int tg_bind_obs(tg_env *env, float *obs);
 
+/* Gym-style flag views: three persistent DEV u8 [N] arrays (4-byte aligned) that every later tg_step also fills with
+ * 0 / 1 bytes -- done != 0, terminated, truncated -- next to the `done` bit mask, so that a host framework can hand them
+ * out as boolean tensors without elementwise kernels of its own.  All three NULL unbinds.  (tg_step_host* and
+ * tg_primitive_step do not write them.) */
+int tg_bind_flags(tg_env *env, uint8_t *done01, uint8_t *terminated01, uint8_t *truncated01);
+
 /* Same, with HOST buffers (pinned recommended): copies actions in, runs the step, copies
  * obs/reward/done(/ran) out and synchronises the stream.  Any output may be NULL. */
 int tg_step_host(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done,
@@ -174,6 +180,18 @@ int tg_available_mask(tg_env *env, uint8_t *mask, void *stream);
 /* TreasureGame.render('rgb_array') (treasure_game.py:98-104 -> drawer.draw_domain :136-163).
  * frames DEV [count][frame_h][frame_w][3] u8 for envs first .. first+count-1. */
 int tg_render(tg_env *env, int64_t first, int64_t count, uint8_t *frames, void *stream);
+
+/* The option layer with a drawer (_option.py:20-36 with :33-34: drawer.draw_domain() after every primitive tick;
+ * create_options(md, drawer), _move_options.py).  The `count` envs env_ids[k] (DEV int64, distinct) take one gym step
+ * with option actions[k] (DEV int32), run tick by tick; frames DEV [count][max_ticks][frame_h][frame_w][3] u8
+ * (16-byte aligned) receives the frame after tick t at [k][t-1]; frames after the option's last tick repeat its final
+ * frame (an option that cannot run yields max_ticks copies of the unchanged state; ticks beyond max_ticks are run but
+ * not drawn).  n_ticks DEV [count] int32 = primitive ticks of the option (0 = not runnable, -1 = bad env id).  obs DEV
+ * [count][obs_dim] / reward / done / ran DEV [count], any of them NULL: the step's results as in tg_step (after an
+ * auto-reset obs is the first observation of the new episode while the frames show the old one).  The other envs of
+ * the batch are not stepped. */
+int tg_step_frames(tg_env *env, const int64_t *env_ids, int32_t count, const int32_t *actions, int32_t max_ticks,
+                   uint8_t *frames, int32_t *n_ticks, float *obs, float *reward, uint8_t *done, uint8_t *ran, void *stream);
 
 /* ---- analysis helpers of the drawer (off the gym path; _treasure_game_drawer.py:165-231) ----
  * _TreasureGameDrawer.blend (:207-231), batched: surface s (s < count / per_surface) receives the envs

@@ -411,7 +411,7 @@ class OracleEnv:
     def mask(self):                      # tg:83-89
         return [int(self.can_run(k)) for k in range(9)]
 
-    def run_option(self, k):             # opt:20-36 with the policies of opts
+    def run_option(self, k, on_tick=None):   # opt:20-36 with the policies of opts; on_tick = drawer.draw_domain (opt:33-34)
         if not self.can_run(k):
             return None
         tot = 0
@@ -465,6 +465,8 @@ class OracleEnv:
             first = False
             tot += self.tick(act)
             n += 1
+            if on_tick is not None:                      # opt:33-34: a frame after every primitive tick
+                on_tick()
             if n >= TICK_CAP and not done:
                 raise ReferenceWouldFail("option does not terminate")
         return tot
@@ -484,8 +486,8 @@ class OracleEnv:
     def is_done(self):                   # tg:95
         return self.has_kind_in_bag(K_GOLD) and self.player_cell()[1] == 0
 
-    def gym_step(self, a):               # tg:91-96
-        r = self.run_option(a)
+    def gym_step(self, a, on_tick=None):     # tg:91-96
+        r = self.run_option(a, on_tick)
         return self.obs(), r, self.is_done(), {}
 
     # ---- save / restore (impl:380-400, impl:447-481) ----------------------
