@@ -591,8 +591,10 @@ extern "C" int tg_step_host_sparse(tg_env *env, const int32_t *actions, float *o
     const int64_t n = env->B.n;
     const int od = env->B.obs_dim;
     static const int forced_chunks = getenv("TG_SPARSE_CHUNKS") ? atoi(getenv("TG_SPARSE_CHUNKS")) : 0;
+    // chunks: the kernel of chunk c + 1 and the copy of chunk c overlap the host-side patching of chunk c - 1 (measured at
+    // 1,048,576 envs, one B200 + 16 host threads: 1 / 2 / 3 / 4 chunks = 0.68 / 0.59 / 0.48 / 0.53 ms per step)
     int chunks = 1;
-    if (n >= (int64_t)4 * 131072) chunks = 2;        // the records are a fifth of the dense outputs: two chunks overlap enough
+    if (n >= (int64_t)6 * 131072) chunks = 3; else if (n >= (int64_t)3 * 131072) chunks = 2;
     if (forced_chunks >= 1 && forced_chunks <= 8) chunks = forced_chunks;
     const int64_t per = ((n + chunks - 1) / chunks + 2047) / 2048 * 2048;
     const int used = (int)((n + per - 1) / per);

@@ -45,7 +45,7 @@ __device__ __forceinline__ void stats_accumulate(int *sh, unsigned long long *gs
 }
 
 #ifndef TG_STEP_THREADS
-#define TG_STEP_THREADS 256
+#define TG_STEP_THREADS 384      // 12 warps x 2 CTAs per SM at 80 registers (256 x 3: 103 -> 99 us per 1,048,576-env step; 512 x 2 at 64 registers spills: 101 us)
 #endif
 constexpr int STEP_THREADS = TG_STEP_THREADS;
 constexpr int AUX_THREADS = 128;       // reset / mask kernels
@@ -124,7 +124,7 @@ __device__ __forceinline__ uint32_t pack_pending(uint32_t drawn, int n, bool jum
 // depend on the order: every env owns its RNG stream and state.
 // ---------------------------------------------------------------------------
 #ifndef TG_STEP_MIN_BLOCKS
-#define TG_STEP_MIN_BLOCKS 3
+#define TG_STEP_MIN_BLOCKS 2
 #endif
 template <bool TAPE, int NI>
 __global__ void __launch_bounds__(STEP_THREADS, TG_STEP_MIN_BLOCKS)
