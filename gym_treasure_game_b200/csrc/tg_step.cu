@@ -364,10 +364,10 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, int cap, const int
         if (done_out) done_out[i] = (uint8_t)d;
         if (ran_out) ran_out[i] = (uint8_t)1;
         if (B.flag_done) { B.flag_done[i] = d ? 1 : 0; B.flag_term[i] = d & 1u; B.flag_trunc[i] = (d >> 1) & 1u; }
-        if (B.phase_ts && lane == 0 && q < 128) {                                 // [grid][8] phase stamps, then [grid][128][4] chunks
+        if (B.phase_ts && lane == 0 && q < 128 && blockIdx.x < 8192) {                                 // [8192][8] phase stamps, then [grid][128][4] chunks
             unsigned long long t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1) :: "memory");
-            unsigned long long *ct = B.phase_ts + (size_t)gridDim.x * 8 + ((size_t)blockIdx.x * 128 + (size_t)q) * 4;
+            unsigned long long *ct = B.phase_ts + (size_t)8192 * 8 + ((size_t)blockIdx.x * 128 + (size_t)q) * 4;
             ct[0] = chunk_t0; ct[1] = (t1 - chunk_t0) | ((unsigned long long)(code[el] / 12) << 32) | ((unsigned long long)n << 40);
             ct[2] = (chunk_t1 - chunk_t0) | ((chunk_t2 - chunk_t1) << 32);
             ct[3] = chunk_t3 ? ((chunk_t3 - chunk_t2) | ((t1 - chunk_t3) << 32)) : 0ull;

@@ -239,9 +239,13 @@ int tg_set_draw_tape(tg_env *env, const double *tape, const int64_t *offsets, vo
 int tg_stats(tg_env *env, int64_t *out8, void *stream);
 int tg_stats_clear(tg_env *env, void *stream);
 
-/* Debug instrumentation: DEV uint64[grid][8] (or NULL to switch off).  When set, thread 0 of every step-kernel CTA
- * writes %globaltimer (ns) at its phase boundaries: start, levels staged, option sort, classified, class sort,
- * options executed, outputs written, statistics done.  Used by tools/bench_phases.py; not part of the reference surface. */
+/* Debug instrumentation: DEV uint64[8192 * 8 + 8192 * 512] (or NULL to switch off).  When set, thread 0 of every
+ * step-kernel CTA (up to 8192) writes %globaltimer (ns) at its phase boundaries into stamps[cta][0..7]: start, levels
+ * staged, phase A done, sorted, its warp left phase B, phase B done, phase C done, statistics done; and lane 0 of the warp
+ * that ran chunk q of the CTA writes, at stamps[8192 * 8 + (cta * 128 + q) * 4 ..]: start time, duration | class << 32 |
+ * ticks << 40, and the durations of the chunk's four segments (load + set-up, option, state + plan, observation +
+ * outputs; two 32-bit values per word).  Used by tools/bench_phases.py and tools/bench_chunks.py; not part of the
+ * reference surface. */
 int tg_debug_phase_buffer(tg_env *env, uint64_t *stamps);
 
 /* Debug / tuning: environments per step-kernel CTA (32..4096, rounded up to a multiple of 4; 0 = automatic, the

@@ -14,19 +14,18 @@ acts = torch.empty((n,), dtype=torch.int32, device="cuda")
 new_actions = lambda: torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device="cuda", out=acts)
 bench.desynchronise(env, torch, new_actions)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-grid_max = 4096
+grid_max = 8192
 stamps = torch.zeros(grid_max * 8 + grid_max * 512, dtype=torch.int64, device="cuda")
 env._L.tg_debug_phase_buffer(env._h, C.c_void_p(stamps.data_ptr()))
 NAMES = ["walk", "ladder", "drop", "jump", "interact"]
-GRID = int(sys.argv[2]) if len(sys.argv) > 2 else 444
 for rep in range(3):
     new_actions(); stamps.zero_(); flush.zero_()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record(); env.step_raw(acts); e.record(); e.synchronize()
-    tile = int(os.environ.get("TG_STEP_TILE", "0")) or None
-    grid = GRID
-    ph = stamps[: grid * 8].view(grid, 8).cpu()
-    ch = stamps[grid * 8: grid * 8 + grid * 512].view(grid, 128, 4).cpu()
+    ph = stamps[: grid_max * 8].view(grid_max, 8)
+    grid = int((ph[:, 0] > 0).sum())
+    ph = ph[:grid].cpu()
+    ch = stamps[grid_max * 8: grid_max * 8 + grid * 512].view(grid, 128, 4).cpu()
     t0 = int(ph[:, 0].min())
     print("rep %d: event %.1f us, %d CTAs; phase B start (median) %.1f us, end median %.1f / max %.1f us" % (
         rep, s.elapsed_time(e) * 1e3, grid, float((ph[:, 3] - t0).float().median()) / 1e3,

@@ -7,18 +7,19 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gym_treasure_game_b200 import VectorTreasureGame
 
-NAMES = ["start", "levels", "phase-A", "sort", "t0-left-B", "phase-B", "stats", ""]
+NAMES = ["start", "levels", "phase-A", "sort", "t0-left-B", "phase-B", "phase-C", "stats"]
 
 
 def run(n, scenario, flush_mb=512, reps=7):
     env = VectorTreasureGame(n, seed=0, render=False, auto_reset=True, max_episode_steps=100)
-    stamps = torch.zeros((8192, 8), dtype=torch.int64, device="cuda")
+    stamps_all = torch.zeros(8192 * 8 + 8192 * 512, dtype=torch.int64, device="cuda")   # phase stamps, then the chunk stamps (bench_chunks.py)
+    stamps = stamps_all[: 8192 * 8].view(8192, 8)
     flush = torch.empty(max(flush_mb, 1) << 20, dtype=torch.uint8, device="cuda")
     g = torch.Generator(device="cuda").manual_seed(1)
     acts = torch.empty((n,), dtype=torch.int32, device="cuda")
     for _ in range(30):
         env.step_raw(torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device="cuda", out=acts))
-    env._L.tg_debug_phase_buffer(env._h, C.c_void_p(stamps.data_ptr()))
+    env._L.tg_debug_phase_buffer(env._h, C.c_void_p(stamps_all.data_ptr()))
     rows = []
     for rep in range(reps):
         if scenario == "random":
