@@ -6,6 +6,8 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstdio>
+#include <algorithm>
+#include <climits>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -87,6 +89,10 @@ struct tg_env {
     int sp_words = 0;
     bool sp_primed = false, sp_dense_flags = false;
     const void *sp_obs = nullptr, *sp_reward = nullptr, *sp_done = nullptr, *sp_ran = nullptr;
+    // mixed-layout batches: per layout the ascending list of its env indices (host copy for the range search, device copy
+    // for the renderer, which draws a mixed batch layout by layout)
+    std::vector<int32_t> lev_envs[TG_MAX_LEVELS];
+    int32_t *d_lev_envs[TG_MAX_LEVELS] = {};
     std::vector<uint32_t> sp_prev;                           // env indices patched by the previous sparse call
 };
 
@@ -360,6 +366,14 @@ extern "C" int tg_create(const tg_level *const *levels, int32_t n_levels, const 
         CUE(dev_alloc(e, &d_ids, (size_t)num_envs));
         CUE(cudaMemcpy(d_ids, level_ids, (size_t)num_envs, cudaMemcpyHostToDevice));
         B.level_id = d_ids;
+        if (num_envs <= INT32_MAX) {
+            for (int64_t i = 0; i < num_envs; i++) e->lev_envs[level_ids[i]].push_back((int32_t)i);
+            for (int l = 0; l < n_levels; l++) {
+                if (e->lev_envs[l].empty()) continue;
+                CUE(dev_alloc(e, &e->d_lev_envs[l], e->lev_envs[l].size()));
+                CUE(cudaMemcpy(e->d_lev_envs[l], e->lev_envs[l].data(), e->lev_envs[l].size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            }
+        }
     }
     {   // quotient tables of the observation (impl:368-378): float32 of the reference's float64 x / width, y / height
         std::vector<float> lut((size_t)n_levels * 2 * OBS_LUT_N);
@@ -691,6 +705,23 @@ extern "C" int tg_render(tg_env *env, int64_t first, int64_t count, uint8_t *fra
     if (reinterpret_cast<uintptr_t>(frames) & 15u) return fail(TG_ERR_ARG, "frames must be 16-byte aligned (bulk stores)");
     if (count == 0) return TG_OK;
     DeviceGuard guard(env->device);
+    bool have_lists = false;
+    for (int l = 0; l < env->n_levels; l++) have_lists = have_lists || !env->lev_envs[l].empty();
+    if (env->B.level_id && have_lists) {
+        // mixed batch: the envs of [first, first + count) layout by layout
+        const int32_t *lists[TG_MAX_LEVELS]; int64_t counts[TG_MAX_LEVELS];
+        int nl = 0;
+        for (int l = 0; l < env->n_levels; l++) {
+            const std::vector<int32_t> &v = env->lev_envs[l];
+            const size_t lo = std::lower_bound(v.begin(), v.end(), (int32_t)first) - v.begin();
+            const size_t hi = std::lower_bound(v.begin(), v.end(), (int32_t)(first + count)) - v.begin();
+            lists[l] = env->d_lev_envs[l] ? env->d_lev_envs[l] + lo : nullptr; counts[l] = (int64_t)(hi - lo);
+            nl += counts[l] > 0;
+        }
+        CU(launch_render(env->B, env->R, first, count, frames, (cudaStream_t)stream, lists, counts));
+        env->launches += nl;
+        return TG_OK;
+    }
     CU(launch_render(env->B, env->R, first, count, frames, (cudaStream_t)stream));
     env->launches += (count + 32767) / 32768;
     return TG_OK;

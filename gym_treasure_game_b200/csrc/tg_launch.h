@@ -50,7 +50,7 @@ cudaError_t launch_mask(const BatchView &B, int ni, uint8_t *mask, cudaStream_t 
 cudaError_t launch_get_state(const BatchView &B, const tg_state_view &v, cudaStream_t s);
 cudaError_t launch_set_state(const BatchView &B, const tg_state_view &v, cudaStream_t s);
 cudaError_t launch_render(const BatchView &B, const RenderView &R, int64_t first, int64_t count,
-                          uint8_t *frames, cudaStream_t s);
+                          uint8_t *frames, cudaStream_t s, const int32_t *const *lists = nullptr, const int64_t *counts = nullptr);
 cudaError_t launch_blend(const BatchView &B, const RenderView &R, int64_t first, int64_t n_surfaces, int64_t per,
                          uint8_t *surfaces, int alpha_objs, int alpha_player, cudaStream_t s);
 cudaError_t launch_blit_alpha(uint8_t *target, int tw, int th, const uint8_t *source, int sw, int sh, int channels,

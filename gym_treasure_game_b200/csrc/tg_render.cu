@@ -370,8 +370,8 @@ __device__ __forceinline__ void tma_store(void *dst, uint32_t src_a, uint32_t by
 //   mode 2: prefix state differs from K*  -> W = pristine rows re-fetched by TMA (L2) + every object
 // Drawing order is preserved: everything outside the prefix comes later in file order, the hero last.
 __global__ void __launch_bounds__(RS_THREADS)
-tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int EB, int64_t first, int64_t count,
-                        uint8_t *__restrict__ frames, unsigned long long *__restrict__ job_counter, int dbg) {
+tg_render_stream_kernel(BatchView B, RenderAssets A, int lid, const int32_t *__restrict__ env_list, int W, int H, int UR, int EB,
+                        int64_t first, int64_t count, uint8_t *__restrict__ frames, unsigned long long *__restrict__ job_counter, int dbg) {
     extern __shared__ __align__(128) uint8_t rs_smem[];
     __shared__ uint64_t bar, bar2;
     __shared__ uint4 s_core[RS_EB_MAX];
@@ -383,12 +383,13 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int E
     __shared__ int s_nobj, s_nhandles, s_nitems, s_votes;
     __shared__ uint16_t s_key[RS_EB_MAX];
     __shared__ uint8_t s_mode[RS_EB_MAX];
+    __shared__ int32_t s_off[RS_EB_MAX];              // frame index of the job's envs (env - first): consecutive, or from env_list
     __shared__ long long s_job;
     const int tid = threadIdx.x;
     const uint32_t unit_bytes = (uint32_t)(UR * W * 3);
     uint8_t *C = rs_smem, *W0 = rs_smem + unit_bytes, *W1 = rs_smem + 2 * (size_t)unit_bytes;
     const uint32_t bar_a = smem_addr(&bar), bar2_a = smem_addr(&bar2);
-    const LevelBlob &L = B.levels[0];
+    const LevelBlob &L = B.levels[lid];               // one layout per launch: a mixed batch is rendered level by level (env_list)
     const uint32_t *spr = A.sprites;
     const int rad = S / 10;                                       // int(xscale / 10), drawer.py:265
 
@@ -450,7 +451,8 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int E
             s_votes = 0;
         }
         if (tid < ne) {
-            const int64_t env = first + e0 + tid;
+            const int64_t env = env_list ? (int64_t)env_list[e0 + tid] : first + e0 + tid;
+            s_off[tid] = (int32_t)(env - first);
             s_core[tid] = B.core[env];
             s_items23[tid] = B.items23 ? B.items23[env] : make_uint2(0u, 0u);
             for (int hnd = 0; hnd < s_nhandles; hnd++) {                          // drawer.py:258-262
@@ -537,7 +539,7 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int E
             s_mode[tid] = (dbg == 1) ? 0 : (!same ? 2 : (dyn ? 1 : 0));
         }
         __syncthreads();
-        uint8_t *job_dst = frames + ((size_t)e0 * H + (size_t)y0) * (size_t)W * 3;
+        uint8_t *row_dst = frames + (size_t)y0 * (size_t)W * 3;       // + frame index * frame_bytes
         const size_t frame_bytes = (size_t)H * W * 3;
 
         if (tid < 32) {
@@ -546,7 +548,7 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int E
                 for (int uidx = 0; uidx < ne; uidx++) {
                     if (s_mode[uidx] != 0) continue;
                     wait_bulk_read(6);
-                    tma_store(job_dst + uidx * frame_bytes, smem_addr(C), unit_bytes);
+                    tma_store(row_dst + (size_t)s_off[uidx] * frame_bytes, smem_addr(C), unit_bytes);
                 }
             }
         } else {
@@ -607,7 +609,7 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int W, int H, int UR, int E
                 patch_barrier();
                 if (pt == 0) {
                     wait_bulk_read(6);
-                    tma_store(job_dst + uidx * frame_bytes, smem_addr(wbuf), unit_bytes);
+                    tma_store(row_dst + (size_t)s_off[uidx] * frame_bytes, smem_addr(wbuf), unit_bytes);
                     lastW[kbuf] = G;
                     G++;
                 }
@@ -643,37 +645,54 @@ static int pick_unit_rows(int W) {
     return 4;
 }
 
+// one launch of the streaming renderer: `count` envs of layout `lid`, consecutive from `first` or listed in env_list
+static cudaError_t launch_stream(const BatchView &B, const RenderView &R, int lid, const int32_t *env_list, int64_t first, int64_t count,
+                                 uint8_t *frames, cudaStream_t s) {
+    const int ur = pick_unit_rows(R.frame_w);
+    const size_t smem = (size_t)3 * ur * R.frame_w * 3;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tg_render_stream_kernel, RS_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    // envs per job: as many as possible (the per-job set-up -- pristine rows, vote, baking -- is amortised
+    // over them: 16384 frames, 32/64/128/256 envs -> 5.27/5.38/5.49/5.61 TB/s) while leaving >= 8 jobs per
+    // resident CTA so that the dynamic job queue still balances (4096 frames: 256 -> 4.3, 64 -> 5.45 TB/s)
+    static int eb_forced = -1;
+    if (eb_forced < 0) { const char *v = getenv("TG_RENDER_EB"); eb_forced = v ? atoi(v) : 0; }
+    const int64_t slots = (int64_t)device_sm_count() * per_sm;
+    int eb = RS_EB_MAX;
+    while (eb > 16 && (int64_t)(R.frame_h / ur) * ((count + eb - 1) / eb) < 8 * slots) eb >>= 1;
+    if (eb_forced >= 16 && eb_forced <= RS_EB_MAX) eb = eb_forced;
+    const int64_t njobs = (int64_t)(R.frame_h / ur) * ((count + eb - 1) / eb);
+    const int64_t grid = njobs < slots ? njobs : slots;
+    static int dbg = -1;
+    if (dbg < 0) { const char *v = getenv("TG_RENDER_DBG"); dbg = v ? atoi(v) : 0; }
+    e = cudaMemsetAsync(R.job_counter, 0, sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    tg_render_stream_kernel<<<(unsigned)grid, RS_THREADS, smem, s>>>(B, R.assets[lid], lid, env_list, R.frame_w, R.frame_h, ur, eb, first, count,
+                                                                     frames, R.job_counter, dbg);
+    return cudaGetLastError();
+}
+
+// Frames of the envs [first, first + count).  Single-layout batches: one launch of the streaming renderer.  Mixed
+// batches: one launch per layout over that layout's envs of the range (lists[l] = their indices, DEV, ascending;
+// counts[l] of them) -- each launch keeps one layout's pristine rows, prefix and sprites, exactly like a single-layout
+// batch (the per-band kernel it replaces re-read the background per frame: 2.95 TB/s).  Without lists (the snapshot
+// batches of tg_step_frames) mixed batches use the per-band kernel.
 cudaError_t launch_render(const BatchView &B, const RenderView &R, int64_t first, int64_t count,
-                          uint8_t *frames, cudaStream_t s) {
+                          uint8_t *frames, cudaStream_t s, const int32_t *const *lists, const int64_t *counts) {
     cudaError_t e = render_configure();
     if (e != cudaSuccess) return e;
     static int force_v1 = -1;
     if (force_v1 < 0) { const char *v = getenv("TG_RENDER_V1"); force_v1 = (v && v[0] == '1') ? 1 : 0; }
-    if (B.n_levels == 1 && !force_v1) {
-        const int ur = pick_unit_rows(R.frame_w);
-        const size_t smem = (size_t)3 * ur * R.frame_w * 3;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tg_render_stream_kernel, RS_THREADS, smem);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) per_sm = 1;
-        // envs per job: as many as possible (the per-job set-up -- pristine rows, vote, baking -- is amortised
-        // over them: 16384 frames, 32/64/128/256 envs -> 5.27/5.38/5.49/5.61 TB/s) while leaving >= 8 jobs per
-        // resident CTA so that the dynamic job queue still balances (4096 frames: 256 -> 4.3, 64 -> 5.45 TB/s)
-        static int eb_forced = -1;
-        if (eb_forced < 0) { const char *v = getenv("TG_RENDER_EB"); eb_forced = v ? atoi(v) : 0; }
-        const int64_t slots = (int64_t)device_sm_count() * per_sm;
-        int eb = RS_EB_MAX;
-        while (eb > 16 && (int64_t)(R.frame_h / ur) * ((count + eb - 1) / eb) < 8 * slots) eb >>= 1;
-        if (eb_forced >= 16 && eb_forced <= RS_EB_MAX) eb = eb_forced;
-        const int64_t njobs = (int64_t)(R.frame_h / ur) * ((count + eb - 1) / eb);
-        const int64_t grid = njobs < slots ? njobs : slots;
-        static int dbg = -1;
-        if (dbg < 0) { const char *v = getenv("TG_RENDER_DBG"); dbg = v ? atoi(v) : 0; }
-        e = cudaMemsetAsync(R.job_counter, 0, sizeof(unsigned long long), s);
-        if (e != cudaSuccess) return e;
-        tg_render_stream_kernel<<<(unsigned)grid, RS_THREADS, smem, s>>>(B, R.assets[0], R.frame_w, R.frame_h, ur, eb, first, count,
-                                                                         frames, R.job_counter, dbg);
-        return cudaGetLastError();
+    if (B.n_levels == 1 && !force_v1) return launch_stream(B, R, 0, nullptr, first, count, frames, s);
+    if (lists && counts && !force_v1) {
+        for (int l = 0; l < B.n_levels; l++) {
+            if (counts[l] <= 0) continue;
+            e = launch_stream(B, R, l, lists[l], first, counts[l], frames, s);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
     }
     const size_t band_bytes = (size_t)S * R.frame_w * 3;
     // grid.y is limited to 65535: render in slabs
