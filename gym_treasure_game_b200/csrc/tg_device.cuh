@@ -1120,9 +1120,10 @@ __device__ __forceinline__ void reset_env(Env<NI> &e, const LevelBlob &L) {
 // rounded float32 quotient equals the float64 quotient rounded to float32 (the quotient is a multiple of
 // 1/(W*2^k) away from every rounding boundary, far more than 2^-53).  The slot layout comes from the level's
 // observation program (LevelBlob::obs_prog), so there is no per-object dispatch here.
+static __device__ __noinline__ float obs_quot_far(int v, int extent) { return __fdiv_rn((float)v, (float)extent); }   // out of line: the division is ~40 instructions and write_obs has a dozen sites
 __device__ __forceinline__ float obs_quot(const float *__restrict__ lut, int v, int extent) {
     const unsigned idx = (unsigned)(v + S);
-    return idx < (unsigned)OBS_LUT_N ? __ldg(lut + idx) : __fdiv_rn((float)v, (float)extent);
+    return idx < (unsigned)OBS_LUT_N ? __ldg(lut + idx) : obs_quot_far(v, extent);
 }
 // Writes the row to `o` and, when given, to `o2` (the sparse record of tg_step_host_sparse): every value is computed once.
 template <int NI>
@@ -1142,6 +1143,7 @@ __device__ __forceinline__ void write_obs(const Env<NI> &e, const LevelBlob &L, 
         for (int k = 9; k < obs_dim; k++) put(k, 0.0f);
         return;
     }
+#pragma unroll 1
     for (int k = 0; k < nk; k++) {
         const int p = L.obs_prog[k], op = p >> 4, i = p & 15;
         float v;
