@@ -671,17 +671,38 @@ __device__ __forceinline__ int walk_safe_bound(const Env<NI> &e, const LevelBlob
 
 // The middle of a drop / jump option: LEFT / RIGHT ticks until the player is within 4 px of the target column
 // (opts:239-244 / 305-314; a jump turns round while it stands blocked, opts:309-312).  This is tick(LEFT / RIGHT)
-// (impl:305-313, 331-354) without the action switch: side probe, noisy() from the cached block, the jump ticker or the
-// fall, pick-ups only when an item shares the column range.  A lane runs these ticks on its own (drops and jumps are
-// 0.04 % of the steps under random actions but the longest serial chains of a tile), so the instructions per tick are
-// what matters.  Returns false when the tick cap was hit.
+// (impl:305-313, 331-354) for a lane that runs alone: drops and jumps are 0.04 % of the steps under random actions but
+// 35-tick serial chains, the longest of a tile and the whole of a small batch's step time.  Every probe of these ticks
+// (side: impl:259-281, up_clear: impl:232-238, can_fall: impl:283-288) looks at cells within two columns and a few rows
+// of the player, and doors do not move during the option: an 8 x 8-cell window of the level around the player is
+// gathered once into two 64-bit registers (solid = WALL or closed door, blocked = anything but OPEN), and a probe is
+// two multiply-shifts and a bit test -- no shared-memory load and no cache key on the tick's dependency chain.
+// Returns 1 when aligned, 0 when the tick cap was hit, -1 when the player is about to leave the window (nothing of
+// that tick has been executed: the general loop continues from the same state).
 template <bool TAPE, int NI>
-__device__ __forceinline__ bool move_until_aligned(Env<NI> &e, const LevelBlob &L, bool jump, int s, int tpx, int &n) {
+__device__ __forceinline__ int move_until_aligned(Env<NI> &e, const LevelBlob &L, bool jump, int s, int tpx, int &n) {
+    const int c0 = min(max(pad_cell(min(e.px, tpx) - 20) - 1, 0), TSTRIDE - 8);
+    const int r0 = min(max(pad_cell(e.py) - 3, 0), TSTRIDE - 8);
+    uint64_t ws = 0, wn = 0;
+#pragma unroll
+    for (int rr = 0; rr < 8; rr++) {
+        const uint32_t D = door_bits(L, e.flags, r0 + rr);
+        ws |= (uint64_t)(((L.row_solid[r0 + rr] | D) >> c0) & 0xFFu) << (8 * rr);
+        wn |= (uint64_t)(((L.row_nonopen[r0 + rr] | D) >> c0) & 0xFFu) << (8 * rr);
+    }
+    auto bit = [&](uint64_t w, int x, int y) -> uint32_t {
+        return (uint32_t)(w >> ((pad_cell(y) - r0) * 8 + (pad_cell(x) - c0))) & 1u;
+    };
+    auto can_fall_w = [&](int x, int y) { return (bit(wn, x - 10, y) | bit(wn, x + 10, y) | bit(wn, x - 10, y + 50) | bit(wn, x + 10, y + 50)) == 0u; };
     while (abs(tpx - e.px) >= 4) {
-        const bool blocked = !side_free_m(e, L, e.px + 16 * s);
+        const int x = e.px, y = e.py;
+        // every cell this tick can look at (x - 20 .. x + 20 after the move, y - 4 .. y + 54 after a 4-px fall) is in the window
+        if (pad_cell(x - 20) < c0 || pad_cell(x + 20) > c0 + 7 || pad_cell(y - 4) < r0 || pad_cell(y + 54) > r0 + 7) return -1;
+        const bool blocked = (bit(ws, x + 16 * s, y + 4) | bit(ws, x + 16 * s, y + 44)) != 0u;
+        const bool cf = can_fall_w(x, y);
         int dir = s;
-        if (jump && blocked && !can_fall_m(e, L)) dir = -s;
-        const bool go = (dir == s) ? !blocked : side_free_m(e, L, e.px + 16 * dir);
+        if (jump && blocked && !cf) dir = -s;
+        const bool go = (dir == s) ? !blocked : (bit(ws, x + 16 * dir, y + 4) | bit(ws, x + 16 * dir, y + 44)) == 0u;
         e.total_actions++;
         int xd = 0, yd = 0;
         if (go) {
@@ -691,18 +712,16 @@ __device__ __forceinline__ bool move_until_aligned(Env<NI> &e, const LevelBlob &
         }
         const int tk = ticker(e.flags);
         if (tk > 0) {                                                                // impl:331-334
-            if (up_clear_m(e, L)) yd = -4;
+            if ((bit(wn, x - 4, y - 4) | bit(wn, x + 4, y - 4) | bit(wn, x - 4, y - 1) | bit(wn, x + 4, y - 1)) == 0u) yd = -4;
             e.flags = set_ticker(e.flags, tk - 1);
-        } else if (can_fall_m(e, L)) {                                               // impl:335-337
+        } else if (cf) {                                                             // impl:335-337
             yd = 4;
         }
         e.px += xd;                                                                  // impl:339
-        if (yd > 0 && can_fall_m(e, L)) {                                            // impl:341-346, as in tick()
-            const int q = mod48(e.py);
-            if (q + yd <= 45) e.py += yd;
-            else do {
+        if (yd > 0 && can_fall_w(e.px, y)) {                                         // impl:341-346: one pixel at a time
+            do {
                 e.py++; yd--;
-                if (!can_fall_m(e, L)) yd = 0;
+                if (!can_fall_w(e.px, e.py)) yd = 0;
             } while (yd > 0);
         } else {
             e.py += yd;                                                              // impl:348
@@ -712,39 +731,59 @@ __device__ __forceinline__ bool move_until_aligned(Env<NI> &e, const LevelBlob &
         for (int i = 0; i < NI; i++) near_x |= (i < L.n_items) && abs(e.px - (e.ix[i] + S / 2)) < 24;
         if (near_x) pickups(e, L);
         n++;
-        if (n >= TG_TICK_CAP) return false;
+        if (n >= TG_TICK_CAP) return 0;
     }
-    return true;
+    row_cache_drop(e);
+    return 1;
 }
 
 // The end of a drop / jump option once the player is aligned with its target column: NOP ticks until it cannot fall
-// (opts:233-238 / 299-304), the last of them on firm ground.  A NOP tick of a falling player (impl:335-348, no jump in
-// progress) moves it down one pixel at a time, at most 4, and stops at the first y where can_fall fails; playerx does
-// not change, so can_fall (impl:283-288: rows of y and y + 50 at x -+ 10 all OPEN) is a function of y alone: the
-// column profile `blk` (bit r = something at x -+ 10 in padded row r, closed doors included) gives the resting y
-// directly, and the fall takes ceil(distance / 4) ticks plus the final one.  No draws.  Returns false (nothing done)
-// when a jump is still rising or a key / coin is within reach of the column (pickups happen tick by tick).
+// (opts:233-238 / 299-304), the last of them executed after the policy has seen firm ground.  playerx does not change
+// any more, so every probe looks at fixed columns and two column profiles (bit r = something at x -+ 10 / x -+ 4 in padded
+// row r, closed doors included) turn them into register bit tests:
+//   * while a jump is still rising (impl:331-334): one tick = 4 px up if up_clear, ticker - 1 -- a loop in registers;
+//   * the fall (impl:335-348, no jump in progress): one pixel at a time, at most 4 per tick, stopping at the first y
+//     where can_fall fails -- the resting y comes from the profile directly and the fall takes ceil(distance / 4) ticks,
+//     plus the final one.
+// No draws.  Returns false (nothing done) when a key / coin is within reach of the column (pickups happen tick by tick).
 template <int NI>
 __device__ __forceinline__ bool fall_to_rest(Env<NI> &e, const LevelBlob &L, int &n) {
-    if (ticker(e.flags) != 0) return false;
 #pragma unroll
     for (int i = 0; i < NI; i++) if (i < L.n_items && abs(e.px - (e.ix[i] + S / 2)) < 24) return false;
-    const int ca = pad_cell(e.px - 10), cb = pad_cell(e.px + 10);
-    uint32_t blk = L.col_nonopen[ca] | L.col_nonopen[cb];
+    const int ca = pad_cell(e.px - 10), cb = pad_cell(e.px + 10), cu = pad_cell(e.px - 4), cv = pad_cell(e.px + 4);
+    uint32_t blk = L.col_nonopen[ca] | L.col_nonopen[cb], upb = L.col_nonopen[cu] | L.col_nonopen[cv];
     const uint32_t closed = (e.flags >> F_DOORS) & 63u;
     for (int d = 0; d < L.n_doors; d++) {
         const int dc = L.door_cx[d] + PAD;
-        if (((closed >> d) & 1u) && (dc == ca || dc == cb)) blk |= 1u << (L.door_cy[d] + PAD);
+        if (!((closed >> d) & 1u)) continue;
+        if (dc == ca || dc == cb) blk |= 1u << (L.door_cy[d] + PAD);
+        if (dc == cu || dc == cv) upb |= 1u << (L.door_cy[d] + PAD);
     }
-    // first y' >= y at which the row of y' or the row of y' + 50 holds something: the padded row r starts at pixel
-    // 48 * (r - PAD); the border rows are WALL, so both searches find a row
-    const int ra = pad_cell(e.py), rb = pad_cell(e.py + 50);
-    const uint32_t ma = blk >> ra, mb = blk >> rb;
-    const int ya = (ma & 1u) ? e.py : S * (ra + __ffs(ma) - 1 - PAD), yb = (mb & 1u) ? e.py : S * (rb + __ffs(mb) - 1 - PAD) - 50;
-    const int ystop = max(e.py, min(ya, yb));
-    const int ticks = (ystop - e.py + 3) / 4 + 1;
+    int tk = ticker(e.flags), py = e.py, ticks = 0;
+    for (;;) {
+        const bool cf = (((blk >> pad_cell(py)) | (blk >> pad_cell(py + 50))) & 1u) == 0u;   // can_fall (impl:283-288)
+        if (tk == 0 && cf) {
+            // first y' >= y at which the row of y' or the row of y' + 50 holds something: the padded row r starts at pixel
+            // 48 * (r - PAD); the border rows are WALL, so both searches find a row
+            const int ra = pad_cell(py), rb = pad_cell(py + 50);
+            const uint32_t ma = blk >> ra, mb = blk >> rb;
+            const int ya = S * (ra + __ffs(ma) - 1 - PAD), yb = S * (rb + __ffs(mb) - 1 - PAD) - 50;
+            const int ystop = max(py, min(ya, yb));
+            ticks += (ystop - py + 3) / 4 + 1;
+            py = ystop;
+            break;
+        }
+        // a NOP tick with the jump still rising, or the final tick on firm ground (which may still rise: impl:331-334)
+        if (tk > 0) {
+            if ((((upb >> pad_cell(py - 4)) | (upb >> pad_cell(py - 1))) & 1u) == 0u) py -= 4;   // up_clear (impl:232-238)
+            tk--;
+        }
+        ticks++;
+        if (!cf) break;
+    }
     if (n + ticks > TG_TICK_CAP) return false;
-    e.py = ystop;
+    e.py = py;
+    e.flags = set_ticker(e.flags, tk);
     n += ticks; e.total_actions += ticks;
     row_cache_drop(e);
     return true;
@@ -938,7 +977,7 @@ __device__ __forceinline__ int run_option_to_end(Env<NI> &e, const LevelBlob &L,
     // taken in closed form by the loop below (fall_to_rest)
     if (valid && !done && k >= TG_DOWN_LEFT) {
         if (k >= TG_JUMP_LEFT && n == 0) { tick<TAPE, NI, false>(e, L, A_JUMP); n++; }
-        if (!move_until_aligned<TAPE>(e, L, k >= TG_JUMP_LEFT, s, tpx, n)) { e.flags |= 1u << F_ERROR; done = true; }
+        if (move_until_aligned<TAPE>(e, L, k >= TG_JUMP_LEFT, s, tpx, n) == 0) { e.flags |= 1u << F_ERROR; done = true; }
     }
     // ---- everything else, and what the loops above left: policy step + general tick, one lane at its own pace ----
     if (valid && !done) general_option_loop<TAPE, NI, INTERACT_OK, true>(e, L, k, s, tpx, n, [](int) {});
