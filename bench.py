@@ -358,7 +358,50 @@ def main():
         return total * Ke / float(dt.item()), (h1 - h0) // Ke, (d1 - d0) // Ke, 1e3 * ts[len(ts) // 2], 1e3 * ts[-1]
 
     dense = time_host(env.step_host)
-    sparse = time_host(env.step_host_sparse)
+    single = time_host(env.step_host_sparse)
+
+    # Headline: the same entry point in its two halves (tg_step_host_sparse_begin / _end) over sub-batches kept in
+    # flight (PipelinedHostEnv; three parts at this size, two for small shards): while the host patches one part's arrays the
+    # others' kernels run and their records cross.  The loop stays closed per part: the actions of a part's step are handed
+    # over after its previous step ended.
+    from gym_treasure_game_b200 import PipelinedHostEnv
+    penv = PipelinedHostEnv(n, first_env_id=lo, device=dev, seed=0, max_episode_steps=MAX_EPISODE_STEPS,
+                            auto_reset=True, render=False)
+    for k, sub in enumerate(penv.envs):
+        gk = torch.Generator(device=dev).manual_seed(4321 + 2 * rank + k)
+        ak = torch.empty((sub.num_envs,), dtype=torch.int32, device=dev)
+        desynchronise(sub, torch, lambda: torch.randint(0, 9, (sub.num_envs,), generator=gk, dtype=torch.int32, device=dev, out=ak))
+    torch.cuda.synchronize()
+
+    def pipelined_steps(count):
+        for k, (plo, phi) in enumerate(penv.ranges):
+            penv.hosts[k]["actions"] = hpool[0][plo:phi]
+            penv.begin(k)
+        for it in range(1, count):
+            for k, (plo, phi) in enumerate(penv.ranges):
+                penv.end(k)                                     # host arrays of half k complete: obs / reward / done / ran
+                penv.hosts[k]["actions"] = hpool[it % len(hpool)][plo:phi]
+                penv.begin(k)
+        for k in range(penv.parts):
+            penv.end(k)
+
+    pipelined_steps(10)                                         # untimed: dense first step, first touch, host threads up
+    barrier()
+    ph0, pd0 = penv.host_traffic()
+    t0 = time.perf_counter()
+    pipelined_steps(Ke)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    ph1, pd1 = penv.host_traffic()
+    pst = penv.stats()
+    sparse = (total * Ke / float(dt.item()), (ph1 - ph0) // Ke, (pd1 - pd0) // Ke, 1e3 * float(dt.item()) / Ke)
+    if pst["errors"]:
+        raise SystemExit("bench.py: pipelined e2e run flagged %d envs" % pst["errors"])
+    parts_in_flight = penv.parts
+    penv.close()
+    del penv
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -372,10 +415,15 @@ def main():
                    "collective": "NCCL all-reduce of int64[8] stats every 100 steps, side stream"},
         "clocks": r["clocks"],
         "e2e": {"value": sparse[0], "unit": UNIT, "h2d_bytes_per_step": sparse[1], "d2h_bytes_per_step": sparse[2], "steps": Ke,
-                "ms_per_step_median_rank0": sparse[3], "ms_per_step_max_rank0": sparse[4],
-                "api": "tg_step_host_sparse (pinned host buffers; H2D actions, chunked step kernels that compact the envs whose outputs "
-                       "changed into records, one D2H copy per chunk of header + records, host threads patch obs/reward/done/ran in "
-                       "place; stream sync inside the call; bytes counted by the library per copy)",
+                "ms_per_step": sparse[3],
+                "parts_in_flight": parts_in_flight,
+                "api": "PipelinedHostEnv = tg_step_host_sparse_begin / _end over sub-batches in flight (pinned host buffers; per "
+                       "part: H2D actions, step kernels that compact the envs whose outputs changed into records, one D2H copy per "
+                       "chunk of header + tile table + records, host threads patch obs/reward/done/ran in place while the other parts "
+                       "run; a part's next actions are handed over after its previous step ended; bytes counted by the library per copy)",
+                "single_call": {"name": "tg_step_host_sparse", "value": single[0], "h2d_bytes_per_step": single[1],
+                                "d2h_bytes_per_step": single[2], "ms_per_step_median_rank0": single[3], "ms_per_step_max_rank0": single[4],
+                                "api": "one batch, one blocking call per step (begin + end back to back)"},
                 "dense_path": {"name": "tg_step_host", "value": dense[0], "h2d_bytes_per_step": dense[1], "d2h_bytes_per_step": dense[2],
                                "ms_per_step_median_rank0": dense[3],
                                "api": "tg_step_host (pinned host buffers; H2D actions, chunked step kernels overlapping the D2H of every "

@@ -29,7 +29,7 @@ def make(env_id=ENV_ID, **kwargs):
 
 
 def __getattr__(name):      # lazy: importing the package must not require torch/CUDA
-    if name in ("VectorTreasureGame", "shard_range", "all_reduce_stats", "OPTION_NAMES", "STAT_NAMES"):
+    if name in ("VectorTreasureGame", "PipelinedHostEnv", "shard_range", "all_reduce_stats", "OPTION_NAMES", "STAT_NAMES"):
         from . import vector_env
         return getattr(vector_env, name)
     if name in ("TreasureGame", "ObservationWrapper"):

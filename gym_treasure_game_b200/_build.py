@@ -10,7 +10,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 SO = os.path.join(PKG, "libtreasure_b200.so")
 SOURCES = ["tg_step.cu", "tg_render.cu", "tg_blend.cu", "tg_capi.cu"]
-HEADERS = ["tg_types.h", "tg_device.cuh", "tg_launch.h", os.path.join("..", "..", "include", "treasure_b200.h")]
+HEADERS = ["tg_types.h", "tg_device.cuh", "tg_launch.h", "tg_host_patch.h", os.path.join("..", "..", "include", "treasure_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fopenmp", "-shared", "-diag-suppress", "550", "-lgomp"]
 

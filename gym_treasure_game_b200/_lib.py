@@ -63,6 +63,8 @@ _SIGNATURES = {
     "tg_bind_flags": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tg_step_host": (C.c_int, [C.c_void_p] * 7),
     "tg_step_host_sparse": (C.c_int, [C.c_void_p] * 7),
+    "tg_step_host_sparse_begin": (C.c_int, [C.c_void_p] * 7),
+    "tg_step_host_sparse_end": (C.c_int, [C.c_void_p]),
     "tg_available_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tg_render": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "tg_step_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 7),
@@ -79,6 +81,7 @@ _SIGNATURES = {
     "tg_stats_clear": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tg_launch_count": (C.c_int64, [C.c_void_p]),
     "tg_host_traffic": (None, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "tg_debug_host_times": (None, [C.c_void_p, C.POINTER(C.c_double)]),
     "tg_debug_phase_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tg_debug_set_step_tile": (C.c_int, [C.c_void_p, C.c_int32]),
 }

@@ -13,8 +13,12 @@
 #include <vector>
 
 #include <omp.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "tg_launch.h"
+#include "tg_host_patch.h"
 
 using namespace tg;
 
@@ -85,15 +89,19 @@ struct tg_env {
     uint32_t *sp_drecs = nullptr;                             // per chunk: 16-byte header (record count) + records
     uint32_t *sp_hrecs = nullptr;                             // the same regions in pinned host memory (cudaHostAlloc)
     cudaEvent_t ev_rec[8] = {}, ev_h2d[8] = {};
+    size_t sp_off[8] = {}, sp_table_off = 0;                  // region offsets (words) of the chunks in flight
+    int sp_grid[8] = {}, sp_tile[8] = {};                     // CTAs and envs per CTA of each chunk's launch
+    int64_t sp_copied[8] = {}, sp_per = 0;                    // between tg_step_host_sparse_begin and _end: records requested per chunk, chunk size
+    int sp_pending = 0, sp_used = 0;                          // 1 = a sparse step is in flight, 2 = begin ran the dense path; chunks in flight
     int64_t sp_guess[8] = {};                                 // records to copy with the header (previous count + margin), < 0 = all
     int sp_words = 0;
-    bool sp_primed = false, sp_dense_flags = false;
+    bool sp_primed = false;
+    double sp_t_enqueue = 0, sp_t_wait = 0, sp_t_patch = 0;   // seconds spent by the sparse host step: enqueueing, waiting for records, patching
     const void *sp_obs = nullptr, *sp_reward = nullptr, *sp_done = nullptr, *sp_ran = nullptr;
     // mixed-layout batches: per layout the ascending list of its env indices (host copy for the range search, device copy
     // for the renderer, which draws a mixed batch layout by layout)
     std::vector<int32_t> lev_envs[TG_MAX_LEVELS];
     int32_t *d_lev_envs[TG_MAX_LEVELS] = {};
-    std::vector<uint32_t> sp_prev;                           // env indices patched by the previous sparse call
 };
 
 extern "C" const char *tg_last_error(void) { return g_err; }
@@ -435,6 +443,7 @@ extern "C" void tg_host_traffic(const tg_env *env, int64_t *h2d_bytes, int64_t *
 // ---------------------------------------------------------------------------
 extern "C" int tg_reset(tg_env *env, const uint8_t *mask, float *obs, void *stream) {
     if (!env) return fail(TG_ERR_ARG, "null env");
+    if (env->sp_pending) return fail(TG_ERR_STATE, "tg_reset between tg_step_host_sparse_begin and _end");
     DeviceGuard guard(env->device);
     CU(launch_reset(env->B, env->ni, mask, obs, (cudaStream_t)stream));
     env->launches++;
@@ -450,6 +459,7 @@ static bool obs_is_current(const tg_env *env, const float *obs) {
 extern "C" int tg_step(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done, uint8_t *ran,
                        uint16_t *avail, void *stream) {
     if (!env || !actions) return fail(TG_ERR_ARG, "null argument");
+    if (env->sp_pending) return fail(TG_ERR_STATE, "tg_step between tg_step_host_sparse_begin and _end");
     DeviceGuard guard(env->device);
     CU(launch_step(env->B, env->ni, env->step_tile, actions, obs, reward, done, ran, avail, (cudaStream_t)stream));
     env->launches++;
@@ -492,6 +502,7 @@ static int ensure_staging(tg_env *env) {
 extern "C" int tg_step_host(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done,
                             uint8_t *ran, void *stream) {
     if (!env || !actions) return fail(TG_ERR_ARG, "null argument");
+    if (env->sp_pending) return fail(TG_ERR_STATE, "tg_step_host between tg_step_host_sparse_begin and _end");
     DeviceGuard guard(env->device);
     int rc = ensure_staging(env);
     if (rc != TG_OK) return rc;
@@ -540,65 +551,30 @@ extern "C" int tg_step_host(tg_env *env, const int32_t *actions, float *obs, flo
     env->obs_sync = obs ? env->s_obs : nullptr;
     // the caller's arrays now hold every env's outputs: tg_step_host_sparse may patch them from here on
     env->sp_primed = obs && reward && done && ran;
-    env->sp_dense_flags = true;
     env->sp_obs = obs; env->sp_reward = reward; env->sp_done = done; env->sp_ran = ran;
-    env->sp_prev.clear();
     return TG_OK;
-}
-
-// Threads for the host-side patching: the host cores divided among the ranks that share the host (LOCAL_WORLD_SIZE of
-// a torchrun launch, else the visible devices), 2..16; TG_HOST_THREADS overrides.  Passed as a num_threads clause because
-// launchers such as torchrun export OMP_NUM_THREADS=1, which would leave one thread to scatter 200 k rows.
-__attribute__((used)) static int host_threads() {   // referenced from OpenMP clauses only (the CUDA front end does not see those)
-    static int t = 0;
-    if (!t) {
-        const char *v = getenv("TG_HOST_THREADS");
-        int want = v ? atoi(v) : 0;
-        if (want < 1) {
-            int share = 0;
-            const char *lw = getenv("LOCAL_WORLD_SIZE");
-            if (lw) share = atoi(lw);
-            if (share < 1 && (cudaGetDeviceCount(&share) != cudaSuccess || share < 1)) { cudaGetLastError(); share = 1; }
-            want = omp_get_num_procs() / share;
-            if (want > 16) want = 16;
-            if (want < 2) want = 2;
-        }
-        t = want > 64 ? 64 : want;
-    }
-    return t;
-}
-
-// Host side of the sparse step: patch the caller's arrays from `n` records (OpenMP: the rows are scattered over
-// tens of megabytes, one thread would spend longer here than the whole dense copy takes).
-static void sparse_apply(const uint32_t *recs, int64_t n, int words, int od, float *obs, float *reward, uint8_t *done,
-                         uint8_t *ran, uint32_t *touched) {
-#pragma omp parallel for schedule(static) num_threads(host_threads()) if (n > 4096)
-    for (int64_t r = 0; r < n; r++) {
-        const uint32_t *rec = recs + r * words;
-        const uint32_t idx = rec[0];
-        if (r + 8 < n) {                                 // four scattered cache lines per record: have them on their way
-            const uint32_t nx = rec[8 * words];
-            __builtin_prefetch(obs + (size_t)nx * od, 1); __builtin_prefetch(&reward[nx], 1);
-            __builtin_prefetch(&done[nx], 1); __builtin_prefetch(&ran[nx], 1);
-        }
-        touched[r] = idx;
-        memcpy(&reward[idx], &rec[1], 4);
-        done[idx] = (uint8_t)(rec[2] & 255u);
-        ran[idx] = (uint8_t)(rec[2] >> 8);
-        memcpy(obs + (size_t)idx * od, rec + 3, (size_t)od * 4);
-    }
 }
 
 // Record region of chunk c, on the device and mirrored in pinned host memory: a 16-byte header whose first word is the
 // record count (the kernel's atomic), then the records.  One copy brings the header and as many records as the previous
 // step produced plus a margin; the count then says whether a second copy is needed (it rarely is: the share of envs
 // that run is stable from step to step).  This removed a count round trip per chunk (0.17 of 0.70 ms per step).
-extern "C" int tg_step_host_sparse(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done,
-                                   uint8_t *ran, void *stream) {
+//
+// The step comes in two halves so that a caller with two batches can keep the device and the bus busy while the host
+// patches: _begin enqueues everything (no host-side wait), _end waits chunk by chunk and patches the caller's arrays.
+extern "C" int tg_step_host_sparse_begin(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done,
+                                         uint8_t *ran, void *stream) {
     if (!env || !actions || !obs || !reward || !done || !ran) return fail(TG_ERR_ARG, "null argument");
-    if (!env->sp_primed || obs != env->sp_obs || reward != env->sp_reward || done != env->sp_done || ran != env->sp_ran)
-        return tg_step_host(env, actions, obs, reward, done, ran, stream);      // first call / other arrays: everything crosses
+    if (env->sp_pending) return fail(TG_ERR_STATE, "tg_step_host_sparse_begin: the previous step has not been ended");
+    if (!env->sp_primed || !env->B.auto_reset || obs != env->sp_obs || reward != env->sp_reward || done != env->sp_done || ran != env->sp_ran) {
+        // first call / other arrays: everything crosses, now.  Also without auto-reset: an env that stays done reports it in
+        // every step without being touched, which the records do not carry.
+        const int rc = tg_step_host(env, actions, obs, reward, done, ran, stream);
+        if (rc == TG_OK) env->sp_pending = 2;
+        return rc;
+    }
     DeviceGuard guard(env->device);
+    const double t_begin = now_s();
     int rc = ensure_staging(env);
     if (rc != TG_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
@@ -614,7 +590,8 @@ extern "C" int tg_step_host_sparse(tg_env *env, const int32_t *actions, float *o
     const int used = (int)((n + per - 1) / per);
     if (!env->sp_drecs) {
         env->sp_words = (3 + od + 3) / 4 * 4;                                   // 16-byte records
-        const size_t total = ((size_t)n + 8) * env->sp_words + 8 * 4;            // records + one header per chunk
+        // records + per chunk: a header and the tile table (two words per CTA; tiles hold >= 32 envs)
+        const size_t total = ((size_t)n + 8) * env->sp_words + 8 * 4 + 2 * ((size_t)n / 32 + 8 * 4);
         CU(dev_alloc(env, &env->sp_drecs, total));
         CU(cudaHostAlloc((void **)&env->sp_hrecs, total * 4, cudaHostAllocDefault));
         for (int c = 0; c < 8; c++) CU(cudaEventCreateWithFlags(&env->ev_rec[c], cudaEventDisableTiming));
@@ -635,59 +612,94 @@ extern "C" int tg_step_host_sparse(tg_env *env, const int32_t *actions, float *o
     }
     env->h2d_bytes += n * (int64_t)sizeof(int32_t);
     env->obs_sync = nullptr;                         // only records leave the device: no device buffer follows this step
-    int64_t copied[8];
+    env->sp_table_off = 0;
     for (int c = 0; c < used; c++) {
         const int64_t lo = (int64_t)c * per, cnt = (lo + per <= n) ? per : n - lo;
         if (c > 0) CU(cudaStreamWaitEvent(s, env->ev_h2d[c], 0));
-        const size_t off = (size_t)lo * words + (size_t)c * 4;                    // region c = header c + the records of chunk c
+        const int tile = pick_step_tile(cnt, env->step_tile);
+        const int grid = (int)((cnt + tile - 1) / tile);
+        // region c = header c (16 bytes: the record count), the tile table of chunk c's launch, the records of chunk c
+        const size_t off = (size_t)lo * words + (size_t)c * 4 + env->sp_table_off;
+        env->sp_off[c] = off; env->sp_grid[c] = grid; env->sp_tile[c] = tile;
+        const size_t tw = (2 * (size_t)grid + 3) & ~(size_t)3;                    // table words, records stay 16-byte aligned
+        env->sp_table_off += tw;
         uint32_t *dreg = env->sp_drecs + off, *hreg = env->sp_hrecs + off;
         CU(cudaMemsetAsync(dreg, 0, 16, s));
         BatchView V = env->B;
         V.r_begin = lo; V.r_count = cnt; V.advance = (c == used - 1) ? 1 : 0;
-        V.sp_count = dreg; V.sp_recs = dreg + 4; V.sp_words = words;
+        V.sp_count = dreg; V.sp_recs = dreg + 4 + tw; V.sp_words = words;
         CU(launch_step(V, env->ni, env->step_tile, env->s_actions, nullptr, nullptr, nullptr, nullptr, nullptr, s));
         env->launches++;
         CU(cudaEventRecord(env->ev_chunk[c], s));
         CU(cudaStreamWaitEvent(env->side, env->ev_chunk[c], 0));
         int64_t guess = env->sp_guess[c] < 0 ? cnt : env->sp_guess[c];
         if (guess > cnt) guess = cnt;
-        copied[c] = guess;
-        CU(cudaMemcpyAsync(hreg, dreg, 16 + (size_t)guess * words * 4, cudaMemcpyDeviceToHost, env->side));
+        env->sp_copied[c] = guess;
+        CU(cudaMemcpyAsync(hreg, dreg, 16 + 4 * tw + (size_t)guess * words * 4, cudaMemcpyDeviceToHost, env->side));
         CU(cudaEventRecord(env->ev_rec[c], env->side));
     }
-    // while the kernels run: clear what the previous call reported (or everything after a dense call)
-    if (env->sp_dense_flags) {
-        memset(reward, 0, (size_t)n * sizeof(float)); memset(done, 0, (size_t)n); memset(ran, 0, (size_t)n);
-        env->sp_dense_flags = false;
-    } else {
-        const int64_t np = (int64_t)env->sp_prev.size();
-        const uint32_t *prev = env->sp_prev.data();
-#pragma omp parallel for schedule(static) num_threads(host_threads()) if (np > 4096)
-        for (int64_t k = 0; k < np; k++) { reward[prev[k]] = 0.0f; done[prev[k]] = 0; ran[prev[k]] = 0; }
-    }
-    env->sp_prev.clear();
+    CU(cudaEventRecord(env->ev_join, env->side));    // later work on the caller's stream comes after the record copies
+    CU(cudaStreamWaitEvent(s, env->ev_join, 0));
+    env->sp_pending = 1; env->sp_used = used; env->sp_per = per;
+    env->sp_t_enqueue += now_s() - t_begin;
+    return TG_OK;
+}
+
+extern "C" int tg_step_host_sparse_end(tg_env *env) {
+    if (!env) return fail(TG_ERR_ARG, "null env");
+    if (!env->sp_pending) return fail(TG_ERR_STATE, "tg_step_host_sparse_end without a begin");
+    if (env->sp_pending == 2) { env->sp_pending = 0; return TG_OK; }             // the dense path ran inside begin
+    env->sp_pending = 0;
+    DeviceGuard guard(env->device);
+    const int64_t n = env->B.n, per = env->sp_per;
+    const int od = env->B.obs_dim, words = env->sp_words, used = env->sp_used;
+    float *obs = (float *)env->sp_obs, *reward = (float *)env->sp_reward;   // the arrays _begin was given (non-const there)
+    uint8_t *done = (uint8_t *)env->sp_done, *ran = (uint8_t *)env->sp_ran;
     for (int c = 0; c < used; c++) {                 // patch chunk c while chunk c + 1 is still running / crossing
         const int64_t lo = (int64_t)c * per, cnt = (lo + per <= n) ? per : n - lo;
-        const size_t off = (size_t)lo * words + (size_t)c * 4;
+        const size_t off = env->sp_off[c];
+        const int grid = env->sp_grid[c];
         uint32_t *dreg = env->sp_drecs + off, *hreg = env->sp_hrecs + off;
+        const size_t tw = (2 * (size_t)grid + 3) & ~(size_t)3;
+        uint32_t *drecs = dreg + 4 + tw, *hrecs = hreg + 4 + tw;
+        const double t_w0 = now_s();
         CU(cudaEventSynchronize(env->ev_rec[c]));
+        const double t_w1 = now_s();
+        env->sp_t_wait += t_w1 - t_w0;
         const int64_t count = hreg[0];
+        const int64_t copied = env->sp_copied[c];
         if (count > cnt) return fail(TG_ERR_STATE, "sparse step: %lld records for a chunk of %lld envs", (long long)count, (long long)cnt);
-        if (count > copied[c]) {                     // the guess was short (e.g. a step in which every env is reset): the rest
-            CU(cudaMemcpyAsync(hreg + 4 + (size_t)copied[c] * words, dreg + 4 + (size_t)copied[c] * words,
-                               (size_t)(count - copied[c]) * words * 4, cudaMemcpyDeviceToHost, env->side));
+        if (count > copied) {                        // the guess was short (e.g. a step in which every env is reset): the rest
+            CU(cudaMemcpyAsync(hrecs + (size_t)copied * words, drecs + (size_t)copied * words,
+                               (size_t)(count - copied) * words * 4, cudaMemcpyDeviceToHost, env->side));
             CU(cudaStreamSynchronize(env->side));
         }
-        env->d2h_bytes += 16 + (copied[c] > count ? copied[c] : count) * words * 4;
-        env->sp_guess[c] = count + count / 8 + (cnt / 256 > 64 ? cnt / 256 : 64);
-        const size_t base = env->sp_prev.size();
-        env->sp_prev.resize(base + (size_t)count);
-        sparse_apply(hreg + 4, count, words, od, obs, reward, done, ran, env->sp_prev.data() + base);
+        env->d2h_bytes += 16 + 4 * (int64_t)tw + (copied > count ? copied : count) * words * 4;
+        env->sp_guess[c] = count + count / 32 + (cnt / 256 > 64 ? cnt / 256 : 64);
+        if (!sparse_apply_tiles(hreg + 4, grid, env->sp_tile[c], lo, cnt, hrecs, words, od, obs, reward, done, ran))
+            return fail(TG_ERR_STATE, "sparse step: a record outside its tile");
+        env->sp_t_patch += now_s() - t_w1;
     }
-    CU(cudaEventRecord(env->ev_join, env->side));
-    CU(cudaStreamWaitEvent(s, env->ev_join, 0));
-    CU(cudaStreamSynchronize(s));
+    // every chunk's record copy has completed, and each waited for its kernel: nothing of this step is left on the device
     return TG_OK;
+}
+
+extern "C" int tg_step_host_sparse(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done,
+                                   uint8_t *ran, void *stream) {
+    const int rc = tg_step_host_sparse_begin(env, actions, obs, reward, done, ran, stream);
+    return rc != TG_OK ? rc : tg_step_host_sparse_end(env);
+}
+
+int tg_visible_devices() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
+    return n;
+}
+
+extern "C" void tg_debug_host_times(tg_env *env, double *out3) {
+    if (!env || !out3) return;
+    out3[0] = env->sp_t_enqueue; out3[1] = env->sp_t_wait; out3[2] = env->sp_t_patch;
+    env->sp_t_enqueue = env->sp_t_wait = env->sp_t_patch = 0;
 }
 
 extern "C" int tg_available_mask(tg_env *env, uint8_t *mask, void *stream) {
@@ -730,6 +742,7 @@ extern "C" int tg_render(tg_env *env, int64_t first, int64_t count, uint8_t *fra
 extern "C" int tg_step_frames(tg_env *env, const int64_t *env_ids, int32_t count, const int32_t *actions, int32_t max_ticks,
                               uint8_t *frames, int32_t *n_ticks, float *obs, float *reward, uint8_t *done, uint8_t *ran, void *stream) {
     if (!env || !env_ids || !actions || !frames || !n_ticks) return fail(TG_ERR_ARG, "null argument");
+    if (env->sp_pending) return fail(TG_ERR_STATE, "tg_step_frames between tg_step_host_sparse_begin and _end");
     if (!env->has_render) return fail(TG_ERR_STATE, "frames need tg_level_set_sprites on every level (and equal grid sizes)");
     if (count < 1 || max_ticks < 1 || (int64_t)count * max_ticks > (int64_t)1 << 24) return fail(TG_ERR_ARG, "count >= 1, max_ticks >= 1, count * max_ticks <= 2^24");
     if (reinterpret_cast<uintptr_t>(frames) & 15u) return fail(TG_ERR_ARG, "frames must be 16-byte aligned (bulk stores)");
@@ -802,6 +815,7 @@ extern "C" int tg_get_state(tg_env *env, const tg_state_view *out, void *stream)
 
 extern "C" int tg_set_state(tg_env *env, const tg_state_view *in, void *stream) {
     if (!env || !in) return fail(TG_ERR_ARG, "null argument");
+    if (env->sp_pending) return fail(TG_ERR_STATE, "tg_set_state between tg_step_host_sparse_begin and _end");
     DeviceGuard guard(env->device);
     CU(launch_set_state(env->B, *in, (cudaStream_t)stream));
     env->launches++;
@@ -812,6 +826,7 @@ extern "C" int tg_set_state(tg_env *env, const tg_state_view *in, void *stream) 
 
 extern "C" int tg_primitive_step(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done, void *stream) {
     if (!env || !actions) return fail(TG_ERR_ARG, "null argument");
+    if (env->sp_pending) return fail(TG_ERR_STATE, "tg_primitive_step between tg_step_host_sparse_begin and _end");
     DeviceGuard guard(env->device);
     CU(launch_primitive(env->B, env->ni, actions, obs, reward, done, (cudaStream_t)stream));
     env->launches++;
@@ -822,6 +837,7 @@ extern "C" int tg_primitive_step(tg_env *env, const int32_t *actions, float *obs
 
 extern "C" int tg_init_with_state(tg_env *env, const double *states, const uint8_t *mask, void *stream) {
     if (!env || !states) return fail(TG_ERR_ARG, "null argument");
+    if (env->sp_pending) return fail(TG_ERR_STATE, "tg_init_with_state between tg_step_host_sparse_begin and _end");
     DeviceGuard guard(env->device);
     CU(launch_init_with_state(env->B, env->ni, states, mask, (cudaStream_t)stream));
     env->launches++;
@@ -832,6 +848,7 @@ extern "C" int tg_init_with_state(tg_env *env, const double *states, const uint8
 
 extern "C" int tg_set_draw_tape(tg_env *env, const double *tape, const int64_t *offsets, void *stream) {
     if (!env) return fail(TG_ERR_ARG, "null env");
+    if (env->sp_pending) return fail(TG_ERR_STATE, "tg_set_draw_tape between tg_step_host_sparse_begin and _end");
     if ((tape == nullptr) != (offsets == nullptr)) return fail(TG_ERR_ARG, "tape and offsets must both be set or both be null");
     DeviceGuard guard(env->device);
     env->B.tape = tape; env->B.tape_off = offsets;

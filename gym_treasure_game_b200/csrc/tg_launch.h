@@ -36,6 +36,7 @@ struct RenderView {
     unsigned long long *job_counter;   // device word used by the streaming renderer to hand out jobs
 };
 
+int pick_step_tile(int64_t n, int forced);     // envs per CTA of a step launch over n envs (forced = 0: automatic)
 cudaError_t launch_step(const BatchView &B, int ni, int forced_tile, const int32_t *actions, float *obs, float *reward,
                         uint8_t *done, uint8_t *ran, uint16_t *avail, cudaStream_t s);
 cudaError_t launch_reset(const BatchView &B, int ni, const uint8_t *mask, float *obs, cudaStream_t s);

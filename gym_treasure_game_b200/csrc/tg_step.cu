@@ -268,8 +268,12 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, int cap, const int
     const int n_run = hist[NBUCKET - 1];                    // exclusive scan: start of the (unused) last bucket = runnable envs
     const int n_idle_rst = n_reset;                         // idle envs to reset; the option lanes append theirs
     __syncthreads();
-    if (tid == STEP_THREADS - 1 && B.sp_count && n_run + n_idle_rst > 0)
-        rec_base = atomicAdd(B.sp_count, (uint32_t)(n_run + n_idle_rst));      // sparse outputs: this tile's block of records
+    if (tid == STEP_THREADS - 1 && B.sp_count) {            // sparse outputs: this tile's block of records, and where it is
+        const uint32_t nrec = (uint32_t)(n_run + n_idle_rst);
+        const uint32_t rb = nrec ? atomicAdd(B.sp_count, nrec) : 0u;
+        rec_base = rb;
+        *reinterpret_cast<uint2 *>(B.sp_count + 4 + 2 * blockIdx.x) = make_uint2(rb, nrec);   // tile table: after the 16-byte header
+    }
     // Chunks of up to 32 envs that never straddle two classes (a warp whose lanes belong to different classes runs their
     // code paths one after the other: the chunk at the ladder / drop / jump / interact border took 100 us): per class,
     // ceil(count / 32) chunks.  Order: drops and jumps first (single lanes on the general tick: the longest chains), then

@@ -116,7 +116,8 @@ struct BatchView {
     const float *obs_lut;        // [n_levels][2][OBS_LUT_N]
     // sparse outputs (tg_step_host_sparse), or sp_count == NULL: one record of sp_words 32-bit words per env whose
     // outputs are not (obs unchanged, reward 0, done 0, ran 0): [0] env index, [1] reward (float bits),
-    // [2] done | ran << 8, [3 ..] observation
+    // [2] done | ran << 8, [3 ..] observation.  sp_count[0] = records of the launch (atomic); sp_count[4 + 2 b], [5 + 2 b] =
+    // first record and number of records of CTA b's tile (its records are contiguous)
     uint32_t *sp_count;
     uint32_t *sp_recs;
     int32_t sp_words;

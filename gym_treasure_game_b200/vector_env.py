@@ -238,6 +238,19 @@ class VectorTreasureGame:
                                           _ptr(host["done"]), _ptr(host["ran"]), self._stream()))
         return host
 
+    def step_host_sparse_begin(self, host: Optional[Dict[str, torch.Tensor]] = None):
+        """First half of ``step_host_sparse`` (``tg_step_host_sparse_begin``): enqueue the action copy, the step kernels
+        and the record copies on the current stream and return without waiting.  Until ``step_host_sparse_end`` the
+        host arrays must stay untouched (the outputs still hold the previous step)."""
+        host = host or self._host or self.make_host_buffers()
+        check(self._L.tg_step_host_sparse_begin(self._h, _ptr(host["actions"]), _ptr(host["obs"]), _ptr(host["reward"]),
+                                                _ptr(host["done"]), _ptr(host["ran"]), self._stream()))
+        return host
+
+    def step_host_sparse_end(self) -> None:
+        """Second half: wait for the records and patch the host arrays given to ``step_host_sparse_begin``."""
+        check(self._L.tg_step_host_sparse_end(self._h))
+
     @property
     def available_mask(self) -> torch.Tensor:
         """``TreasureGame.available_mask`` (treasure_game.py:83-89): (N, 9) uint8."""
@@ -400,6 +413,62 @@ class VectorTreasureGame:
     @property
     def launch_count(self) -> int:
         return int(self._L.tg_launch_count(self._h))
+
+
+class PipelinedHostEnv:
+    """``num_envs`` environments as ``parts`` sub-batches kept in flight together -- the double-buffered vector env of an
+    actor loop with host-side policies.  Sub-batch k owns a contiguous slice of the global env ids (same streams and
+    results as one ``VectorTreasureGame`` over the whole range: Philox streams are keyed by global env id), its own
+    CUDA stream and its own pinned host arrays ``hosts[k]``.  The loop::
+
+        for k in range(env.parts): env.begin(k)          # actions in env.hosts[k]["actions"]
+        while training:
+            for k in range(env.parts):
+                env.end(k)                               # hosts[k] now holds obs / reward / done / ran of its step
+                ... choose hosts[k]["actions"] from hosts[k]["obs"] ...
+                env.begin(k)                             # runs on the device while the host works on the other parts
+
+    keeps the closed loop per sub-batch (the actions of a step may depend on that sub-batch's last observations)
+    while the device and the bus work on one part and the host patches another."""
+
+    def __init__(self, num_envs: int, parts: Optional[int] = None, first_env_id: int = 0, **kwargs):
+        # measured on one B200 + 16 host cores: 1,048,576 envs 2 / 3 / 4 parts = 0.32 / 0.29 / 0.37 ms per step, 131,072 envs 0.12 / 0.15 / 0.18
+        self.num_envs = int(num_envs)
+        self.parts = int(parts) if parts else (3 if self.num_envs >= 6 * 131072 else 2)
+        self.ranges = [shard_range(self.num_envs, k, self.parts) for k in range(self.parts)]
+        self.envs = [VectorTreasureGame(hi - lo, first_env_id=first_env_id + lo, **kwargs) for lo, hi in self.ranges]
+        self.streams = [torch.cuda.Stream(device=e.device) for e in self.envs]
+        self.hosts = [e.make_host_buffers() for e in self.envs]
+
+    def reset(self):
+        """Reset every sub-batch and fill the host arrays (observations of the initial states, zero flags)."""
+        for e, h in zip(self.envs, self.hosts):
+            h["obs"].copy_(e.reset())
+            h["reward"].zero_(); h["done"].zero_(); h["ran"].zero_()
+        return self.hosts
+
+    def begin(self, k: int) -> None:
+        with torch.cuda.stream(self.streams[k]):
+            self.envs[k].step_host_sparse_begin(self.hosts[k])
+
+    def end(self, k: int):
+        self.envs[k].step_host_sparse_end()
+        return self.hosts[k]
+
+    def stats(self) -> Dict[str, int]:
+        out: Dict[str, int] = {}
+        for e in self.envs:
+            for key, v in e.stats().items():
+                out[key] = out.get(key, 0) + v
+        return out
+
+    def host_traffic(self):
+        t = [e.host_traffic() for e in self.envs]
+        return sum(a for a, _ in t), sum(b for _, b in t)
+
+    def close(self):
+        for e in self.envs:
+            e.close()
 
 
 def all_reduce_stats(stats: torch.Tensor) -> torch.Tensor:

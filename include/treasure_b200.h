@@ -174,6 +174,21 @@ int tg_step_host(tg_env *env, const int32_t *actions, float *obs, float *reward,
 int tg_step_host_sparse(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done,
                         uint8_t *ran, void *stream);
 
+/* tg_step_host_sparse in two halves, for callers that keep two (or more) batches in flight -- the double-buffered
+ * vector env of an actor loop: while the host patches batch A's arrays, batch B's kernels run and its records cross.
+ * _begin enqueues the action copy, the step kernels and the record copies and returns without waiting (a first call /
+ * other arrays run tg_step_host inside _begin instead); _end waits for the records chunk by chunk and patches the
+ * arrays given to _begin.  Contract between the two calls: `actions` and the four output arrays stay untouched (the
+ * outputs still hold the previous step's results), no other state-changing call on this env (they return
+ * TG_ERR_STATE), and each env in flight has its own `stream`.  tg_step_host_sparse == _begin followed by _end. */
+int tg_step_host_sparse_begin(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done,
+                              uint8_t *ran, void *stream);
+int tg_step_host_sparse_end(tg_env *env);
+
+/* Debug: seconds the sparse host step has spent enqueueing (_begin), waiting for records and patching (_end) since the
+ * last call of this function (then reset).  out3 HOST double[3]. */
+void tg_debug_host_times(tg_env *env, double *out3);
+
 /* TreasureGame.available_mask (treasure_game.py:83-89).  mask DEV [N][9] u8. */
 int tg_available_mask(tg_env *env, uint8_t *mask, void *stream);
 

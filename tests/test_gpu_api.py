@@ -82,6 +82,79 @@ def test_step_host_sparse_equals_dense(n):
     assert a.stats() == b.stats()
 
 
+@pytest.mark.parametrize("n,parts", [(5000, 2), (300001, 2), (40000, 3)])
+def test_pipelined_host_env_equals_one_batch(n, parts):
+    """PipelinedHostEnv (tg_step_host_sparse_begin / _end over sub-batches in flight on their own streams) delivers, part
+    by part, what one batch over the whole id range delivers through tg_step_host -- every step, resets included."""
+    import torch
+    from gym_treasure_game_b200 import PipelinedHostEnv, VectorTreasureGame
+    p = PipelinedHostEnv(n, parts=parts, first_env_id=1000, seed=5, max_episode_steps=7, auto_reset=True, render=False)
+    b = VectorTreasureGame(n, first_env_id=1000, seed=5, max_episode_steps=7, auto_reset=True, render=False)
+    hb = b.make_host_buffers()
+    g = torch.Generator().manual_seed(3)
+    acts = [torch.randint(0, 9, (n,), generator=g, dtype=torch.int32) for _ in range(20)]
+    pinned = [a.pin_memory() for a in acts]
+    for k, (lo, hi) in enumerate(p.ranges):
+        p.hosts[k]["actions"] = pinned[0][lo:hi]
+        p.begin(k)
+    for t in range(20):
+        hb["actions"].copy_(acts[t])
+        b.step_host(hb)
+        for k, (lo, hi) in enumerate(p.ranges):
+            h = p.end(k)
+            for key in ("obs", "reward", "done", "ran"):
+                assert torch.equal(h[key], hb[key][lo:hi]), (t, k, key)
+            if t + 1 < 20:
+                p.hosts[k]["actions"] = pinned[t + 1][lo:hi]
+                p.begin(k)
+    assert p.stats() == b.stats()
+    h2d, d2h = p.host_traffic()
+    assert h2d == 20 * n * 4 and d2h < 0.6 * b.host_traffic()[1]
+    p.close(); b.close()
+
+
+def test_sparse_begin_end_contract():
+    """Between _begin and _end every other state-changing call on the env is refused; _end needs a _begin."""
+    import torch
+    from gym_treasure_game_b200 import VectorTreasureGame
+    from gym_treasure_game_b200._lib import TreasureError
+    e = VectorTreasureGame(3000, seed=1, max_episode_steps=9, auto_reset=True, render=False)
+    h = e.make_host_buffers()
+    h["actions"].zero_()
+    with pytest.raises(TreasureError):
+        e.step_host_sparse_end()
+    e.step_host_sparse(h)                             # primes the arrays (dense first call)
+    e.step_host_sparse_begin(h)
+    with pytest.raises(TreasureError):
+        e.step_host_sparse_begin(h)
+    with pytest.raises(TreasureError):
+        e.step(torch.zeros(3000, dtype=torch.int32, device="cuda"))
+    with pytest.raises(TreasureError):
+        e.reset()
+    e.step_host_sparse_end()
+    e.step(torch.zeros(3000, dtype=torch.int32, device="cuda"))    # allowed again
+    e.close()
+
+
+def test_step_host_sparse_without_auto_reset():
+    """Without auto-reset a finished env reports done in every step without being touched; the sparse entry point must
+    deliver that too (it takes the dense path)."""
+    import torch
+    from gym_treasure_game_b200 import VectorTreasureGame
+    n = 6000
+    a = VectorTreasureGame(n, seed=2, max_episode_steps=5, auto_reset=False, render=False)
+    b = VectorTreasureGame(n, seed=2, max_episode_steps=5, auto_reset=False, render=False)
+    ha, hb = a.make_host_buffers(), b.make_host_buffers()
+    g = torch.Generator().manual_seed(9)
+    for t in range(12):
+        acts = torch.randint(0, 9, (n,), generator=g, dtype=torch.int32)
+        ha["actions"].copy_(acts); hb["actions"].copy_(acts)
+        a.step_host_sparse(ha); b.step_host(hb)
+        for k in ("obs", "reward", "done", "ran"):
+            assert torch.equal(ha[k], hb[k]), (t, k)
+    assert int(ha["done"].ne(0).sum()) == n            # past the time limit every env stays done
+
+
 def test_step_host_sparse_mixed_layouts():
     """Sparse records with several layouts in one batch: observation rows of different lengths (zero padded),
     the generic observation program and the 4-item kernels."""

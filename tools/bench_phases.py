@@ -17,12 +17,16 @@ def run(n, scenario, flush_mb=512, reps=7):
     flush = torch.empty(max(flush_mb, 1) << 20, dtype=torch.uint8, device="cuda")
     g = torch.Generator(device="cuda").manual_seed(1)
     acts = torch.empty((n,), dtype=torch.int32, device="cuda")
-    for _ in range(30):
-        env.step_raw(torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device="cuda", out=acts))
+    if scenario == "steady":      # the bench workload: desynchronised episodes, 1 % resets per step
+        import bench
+        bench.desynchronise(env, torch, lambda: torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device="cuda", out=acts))
+    else:
+        for _ in range(30):
+            env.step_raw(torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device="cuda", out=acts))
     env._L.tg_debug_phase_buffer(env._h, C.c_void_p(stamps_all.data_ptr()))
     rows = []
     for rep in range(reps):
-        if scenario == "random":
+        if scenario in ("random", "steady"):
             torch.randint(0, 9, (n,), generator=g, dtype=torch.int32, device="cuda", out=acts)
         else:
             env.reset(); acts.fill_(2)          # up_ladder at the start cell: nothing is runnable
@@ -46,7 +50,11 @@ def run(n, scenario, flush_mb=512, reps=7):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        for n in (4096, 131072, 1 << 20):
+            run(n, sys.argv[1], 512)
+        sys.exit(0)
     for n in (4096, 1 << 20):
-        for sc in ("not_runnable", "random"):
+        for sc in ("not_runnable", "random", "steady"):
             for fl in (512, 0):
                 run(n, sc, fl)
