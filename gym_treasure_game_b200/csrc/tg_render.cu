@@ -385,6 +385,7 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int lid, const int32_t *__r
     __shared__ uint8_t s_mode[RS_EB_MAX];
     __shared__ int32_t s_off[RS_EB_MAX];              // frame index of the job's envs (env - first): consecutive, or from env_list
     __shared__ long long s_job;
+    __shared__ uint16_t s_torder[320];               // unit types in job order: the ones a lever touches first
     const int tid = threadIdx.x;
     const uint32_t unit_bytes = (uint32_t)(UR * W * 3);
     uint8_t *C = rs_smem, *W0 = rs_smem + unit_bytes, *W1 = rs_smem + 2 * (size_t)unit_bytes;
@@ -406,6 +407,27 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int lid, const int32_t *__r
             else if (kind == TG_HANDLE) { cx = L.handle_cx[i]; cy = L.handle_cy[i]; }
             else { cx = L.item_cx[i]; cy = L.item_cy[i]; s_item_init[i] = make_short2((short)(cx * S), (short)(cy * S)); }
             s_obj[o] = make_short4((short)(cx * S), (short)(cy * S), (short)kind, (short)i);
+        }
+        {   // unit types in job order: lever rows spread evenly among the others, none of them among the last types
+            const int nt = H / UR;
+            int nl = 0;
+            auto is_lever = [&](int t) {
+                bool lever = false;
+                for (int hnd = 0; hnd < L.n_handles; hnd++) {
+                    const int oy = L.handle_cy[hnd] * S;
+                    lever = lever || (oy + S + 3 > t * UR && oy < t * UR + UR);
+                }
+                return lever;
+            };
+            for (int t = 0; t < nt; t++) nl += is_lever(t) ? 1 : 0;
+            const int every = nl ? max(1, (nt - nl - 4) / nl) : nt;         // clean types between two lever types
+            int k = 0, tl = 0, tc = 0, run = every;                           // next lever / clean type to place
+            while (k < nt) {
+                while (tl < nt && !is_lever(tl)) tl++;
+                while (tc < nt && is_lever(tc)) tc++;
+                if (tl < nt && (run >= every || tc >= nt)) { s_torder[k++] = (uint16_t)tl++; run = 0; }
+                else { s_torder[k++] = (uint16_t)tc++; run++; }
+            }
         }
         // filled-circle spans of pygame 1.9.x draw_fillellipse(rx = ry = rad), recorded per row
         for (int i = 0; i < 2 * rad; i++) { disc_lo[i] = 127; disc_hi[i] = -128; }
@@ -439,7 +461,10 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int lid, const int32_t *__r
         __syncthreads();
         const int64_t job = s_job;
         if (job >= njobs) break;
-        const int t = (int)(job / nblocks), blk = (int)(job % nblocks);
+        // unit type major, types permuted: a lever-row job composes every unit (two working copies = 64 KB of stores in flight
+        // per CTA against the streamer's seven), so lever rows are spread among the plain rows instead of having every
+        // resident CTA in them at the same time.
+        const int t = s_torder[(int)(job / nblocks)], blk = (int)(job % nblocks);
         const int64_t e0 = (int64_t)blk * EB;
         const int ne = (int)min((int64_t)EB, count - e0);
         const int y0 = t * UR;
@@ -571,7 +596,7 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int lid, const int32_t *__r
                 patch_barrier();
                 if (mode == 2) {
                     mbar_wait(bar2_a, parity2);
-                } else {                             // working copy <- C
+                } else if (dbg != 2) {               // working copy <- C
                     const uint4 *src4 = reinterpret_cast<const uint4 *>(C);
                     uint4 *dst4 = reinterpret_cast<uint4 *>(wbuf);
                     for (uint32_t q = pt; q < unit_bytes / 16; q += RS_PATCH_THREADS) dst4[q] = src4[q];
@@ -598,7 +623,7 @@ tg_render_stream_kernel(BatchView B, RenderAssets A, int lid, const int32_t *__r
                     } else {
                         if (rows_hit(ob.y, 0, 3)) {    // lever rows: oy+8 .. oy+50 (uniform branch)
                             patch_barrier();
-                            lever_pixels(u, ob.x + S / 2, ob.y + S, s_lever[uidx][i].x, s_lever[uidx][i].y, rad, disc_lo, disc_hi);
+                            if (dbg != 3) lever_pixels(u, ob.x + S / 2, ob.y + S, s_lever[uidx][i].x, s_lever[uidx][i].y, rad, disc_lo, disc_hi);
                             patch_barrier();
                         }
                         blit_cols(u, spr + TG_SPR_HANDLE_BASE * S * S, ob.x, ob.y);

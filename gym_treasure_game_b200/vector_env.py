@@ -238,13 +238,14 @@ class VectorTreasureGame:
                                           _ptr(host["done"]), _ptr(host["ran"]), self._stream()))
         return host
 
-    def step_host_sparse_begin(self, host: Optional[Dict[str, torch.Tensor]] = None):
+    def step_host_sparse_begin(self, host: Optional[Dict[str, torch.Tensor]] = None, stream: Optional["torch.cuda.Stream"] = None):
         """First half of ``step_host_sparse`` (``tg_step_host_sparse_begin``): enqueue the action copy, the step kernels
-        and the record copies on the current stream and return without waiting.  Until ``step_host_sparse_end`` the
-        host arrays must stay untouched (the outputs still hold the previous step)."""
+        and the record copies on ``stream`` (default: the current stream) and return without waiting.  Until
+        ``step_host_sparse_end`` the host arrays must stay untouched (the outputs still hold the previous step)."""
         host = host or self._host or self.make_host_buffers()
+        st = self._stream() if stream is None else C.c_void_p(stream.cuda_stream)
         check(self._L.tg_step_host_sparse_begin(self._h, _ptr(host["actions"]), _ptr(host["obs"]), _ptr(host["reward"]),
-                                                _ptr(host["done"]), _ptr(host["ran"]), self._stream()))
+                                                _ptr(host["done"]), _ptr(host["ran"]), st))
         return host
 
     def step_host_sparse_end(self) -> None:
@@ -448,8 +449,9 @@ class PipelinedHostEnv:
         return self.hosts
 
     def begin(self, k: int) -> None:
-        with torch.cuda.stream(self.streams[k]):
-            self.envs[k].step_host_sparse_begin(self.hosts[k])
+        # whatever the caller queued for this sub-batch on the current stream (reset, set_state) comes first
+        self.streams[k].wait_stream(torch.cuda.current_stream(self.envs[k].device))
+        self.envs[k].step_host_sparse_begin(self.hosts[k], self.streams[k])
 
     def end(self, k: int):
         self.envs[k].step_host_sparse_end()
