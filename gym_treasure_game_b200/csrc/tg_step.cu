@@ -276,7 +276,7 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, int cap, const int
     }
     // Chunks of up to 32 envs that never straddle two classes (a warp whose lanes belong to different classes runs their
     // code paths one after the other: the chunk at the ladder / drop / jump / interact border took 100 us): per class,
-    // ceil(count / 32) chunks.  Order: drops and jumps first (single lanes on the general tick: the longest chains), then
+    // ceil(count / 32) chunks.  Order: drops, jumps and interact first (the longest serial chains, and the interact tick's cold code path), then
     // longest first across classes (a chunk's first env is its longest: length is the minor sort key).
     if (tid < 32) {
         const int cs = lane < 5 ? hist[12 * lane] : n_run, ce = lane < 5 ? hist[12 * (lane + 1)] : n_run;   // class lane = perm[cs .. ce)
@@ -289,7 +289,7 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, int cap, const int
         for (int t = 0; t < nch; t++) {
             cstart[q0 + t] = (uint16_t)(cs + 32 * t);
             clen[q0 + t] = (uint8_t)min(32, ce - cs - 32 * t);
-            ckey[q0 + t] = (uint8_t)(11 - code[perm[cs + 32 * t]] % 12 + ((lane == 2 || lane == 3) ? 12 : 0));
+            ckey[q0 + t] = (uint8_t)(11 - code[perm[cs + 32 * t]] % 12 + ((lane >= 2 && lane <= 4) ? 12 : 0));
         }
         if (lane == 0) n_chunks = nq;
         __syncwarp();
