@@ -44,8 +44,8 @@ for rep in range(3):
             NAMES[c], float(m.sum()) / grid, float(d.mean()), float(d.median()), float(d.quantile(0.9)), float(d.max()), float(nt[m].float().mean()),
             float(seg[0].median()), float(seg[1].median()), float(seg[2].median()), float(seg[3].median())))
     tot = (dur * valid).sum(1)
-    print("   sum of chunk durations per CTA: mean %.1f us (/8 warps = %.1f), longest chunk per CTA: mean %.1f us" % (
-        float(tot.mean()), float(tot.mean()) / 8, float((dur * valid).max(1).values.mean())))
+    print("   sum of chunk durations per CTA: mean %.1f us (/12 warps = %.1f), longest chunk per CTA: mean %.1f us" % (
+        float(tot.mean()), float(tot.mean()) / 12, float((dur * valid).max(1).values.mean())))
     # slowest CTA
     k = int((ph[:, 5]).argmax())
     rel0 = (ch[k, :, 0] - int(ph[k, 3])).float() / 1e3
