@@ -690,12 +690,6 @@ extern "C" int tg_step_host_sparse(tg_env *env, const int32_t *actions, float *o
     return rc != TG_OK ? rc : tg_step_host_sparse_end(env);
 }
 
-int tg_visible_devices() {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
-    return n;
-}
-
 extern "C" void tg_debug_host_times(tg_env *env, double *out3) {
     if (!env || !out3) return;
     out3[0] = env->sp_t_enqueue; out3[1] = env->sp_t_wait; out3[2] = env->sp_t_patch;

@@ -5,7 +5,6 @@
 #include <random>
 #include <vector>
 #include "tg_host_patch.h"
-int tg_visible_devices() { return 1; }
 int main(int argc, char **argv) {
     const int64_t n = argc > 1 ? atoll(argv[1]) : 1 << 20;
     const int tile = 3544, od = 9, words = 12, steps = 30;
