@@ -58,6 +58,7 @@ struct tg_level {
     tg_level_info info;
     std::vector<uint8_t> background;   // frame_h * frame_w * 3
     std::vector<uint32_t> sprites;     // TG_NUM_SPRITES * 48 * 48
+    std::vector<uint32_t> closure;     // LevelBlob::closure, built once per level
 };
 
 struct tg_env {
@@ -115,6 +116,69 @@ extern "C" int tg_device_count(void) {
 // ---------------------------------------------------------------------------
 // level compiler (host)
 // ---------------------------------------------------------------------------
+// LevelBlob::closure: set_val (objs:145-149, :175-178, :231-235) followed by process_trigger (objs:76-94) for every
+// (object o, value v, door / handle / bolt bits), for an env whose handles carry no sticky previously_triggered flag.  The
+// walk below is the device's trigger_dfs (tg_device.cuh) step for step: same lists, same order, same blocking set; instead
+// of drawing it records the handles whose angle is redrawn.
+static void build_closure(const LevelBlob &b, std::vector<uint32_t> &tab) {
+    const int nobj = b.n_objs;
+    const uint32_t NB = 1u << CLOSURE_BITS;
+    tab.assign((size_t)nobj * 2 * NB, 7u << CLOSURE_BITS);                // not tabulated
+    auto bit_of = [&](int o) {
+        const int k = b.obj_kind[o], i = b.obj_idx[o];
+        return (k == TG_DOOR) ? i : (k == TG_HANDLE) ? TG_MAX_DOORS + i : TG_MAX_DOORS + TG_MAX_HANDLES + i;
+    };
+    uint32_t valid = 0;
+    for (int o = 0; o < nobj; o++) if (b.obj_kind[o] == TG_DOOR || b.obj_kind[o] == TG_HANDLE || b.obj_kind[o] == TG_BOLT) valid |= 1u << bit_of(o);
+    for (int o0 = 0; o0 < nobj; o0++) {
+        if (!(b.obj_kind[o0] == TG_DOOR || b.obj_kind[o0] == TG_HANDLE || b.obj_kind[o0] == TG_BOLT)) continue;
+        for (int v0 = 0; v0 < 2; v0++)
+            for (uint32_t f0 = 0; f0 < NB; f0++) {
+                if (f0 & ~valid) continue;
+                uint32_t f = f0, events = 0;
+                int ne = 0;
+                bool overflow = false;
+                auto apply = [&](int o, bool v) {
+                    const int bit = bit_of(o);
+                    if ((bool)((f >> bit) & 1u) == v) return false;
+                    f ^= 1u << bit;
+                    if (b.obj_kind[o] == TG_HANDLE) {
+                        if (ne < 5) events |= ((uint32_t)b.obj_idx[o] | (v ? 4u : 0u)) << (3 * ne);
+                        else overflow = true;
+                        ne++;
+                    }
+                    return true;
+                };
+                if (apply(o0, v0 != 0)) {
+                    int st_obj[TG_MAX_OBJECTS + 1], st_t[TG_MAX_OBJECTS + 1], sp = 0;
+                    uint32_t pt = 1u << o0;
+                    st_obj[0] = o0; st_t[0] = b.trig_begin[2 * o0 + v0]; sp = 1;
+                    while (sp > 0) {
+                        const int l = sp - 1, o = st_obj[l];
+                        int t = st_t[l];
+                        const int tend = b.trig_begin[2 * o + (int)((f >> bit_of(o)) & 1u) + 1];
+                        bool pushed = false;
+                        while (t < tend) {
+                            const int ent = b.trig_list[t++];
+                            const int dst = ent & 127; const bool dv = (ent >> 7) != 0;
+                            if (pt & (1u << dst)) continue;
+                            if (apply(dst, dv)) {
+                                st_t[l] = t;
+                                pt |= 1u << dst;
+                                st_obj[sp] = dst; st_t[sp] = b.trig_begin[2 * dst + (dv ? 1 : 0)];
+                                sp++;
+                                pushed = true;
+                                break;
+                            }
+                        }
+                        if (!pushed) { pt &= ~(1u << o); sp--; }
+                    }
+                }
+                if (!overflow) tab[(((size_t)o0 * 2 + v0) << CLOSURE_BITS) | f0] = f | ((uint32_t)ne << CLOSURE_BITS) | (events << 16);
+            }
+    }
+}
+
 extern "C" int tg_level_create(const uint8_t *tiles, int32_t cw, int32_t ch, const tg_object *objs, int32_t n_objs,
                                const tg_trigger *trigs, int32_t n_trigs, tg_level **out) {
     if (!tiles || !out || (n_objs > 0 && !objs) || (n_trigs > 0 && !trigs)) return fail(TG_ERR_ARG, "null argument");
@@ -259,6 +323,7 @@ extern "C" int tg_level_create(const uint8_t *tiles, int32_t cw, int32_t ch, con
     tg_level_info &I = lv->info;
     I.cw = cw; I.ch = ch; I.n_doors = b.n_doors; I.n_handles = b.n_handles; I.n_bolts = b.n_bolts; I.n_items = n_items;
     I.n_objects = n_objs; I.n_triggers = n_trigs; I.obs_dim = obs; I.frame_w = cw * S; I.frame_h = ch * S; I.has_sprites = 0;
+    build_closure(b, lv->closure);
     *out = lv;
     return TG_OK;
 }
@@ -353,7 +418,17 @@ extern "C" int tg_create(const tg_level *const *levels, int32_t n_levels, const 
 
     LevelBlob *d_levels = nullptr;
     CUE(dev_alloc(e, &d_levels, (size_t)n_levels));
-    for (int l = 0; l < n_levels; l++) CUE(cudaMemcpy(d_levels + l, &levels[l]->blob, sizeof(LevelBlob), cudaMemcpyHostToDevice));
+    static const bool no_closure = getenv("TG_NO_CLOSURE") != nullptr;     // debug: every interact walks the trigger graph
+    for (int l = 0; l < n_levels; l++) {
+        LevelBlob blob = levels[l]->blob;
+        if (!levels[l]->closure.empty() && !no_closure) {               // the trigger closure lives in global memory, the blob points to it
+            uint32_t *d_cl = nullptr;
+            CUE(dev_alloc(e, &d_cl, levels[l]->closure.size()));
+            CUE(cudaMemcpy(d_cl, levels[l]->closure.data(), levels[l]->closure.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            blob.closure = d_cl;
+        }
+        CUE(cudaMemcpy(d_levels + l, &blob, sizeof(LevelBlob), cudaMemcpyHostToDevice));
+    }
     B.levels = d_levels;
     CUE(dev_alloc(e, &B.core, (size_t)num_envs));
     CUE(dev_alloc(e, &B.acct, (size_t)num_envs));

@@ -348,8 +348,24 @@ __device__ __forceinline__ void trigger_dfs(Env<NI> &e, const LevelBlob &L, int 
 }
 
 // set_val (objs:145-149, :175-178, :231-235): nothing happens unless the value changes
+// Without sticky handles the whole walk is a function of (o0, v0, door / handle / bolt bits): it is tabulated per level on the
+// host (LevelBlob::closure, tg_capi.cu build_closure), and what is left here is one load, the new bits and the angle draws
+// of the handles that moved, in the walk's order.  The walk itself stays for envs that init_with_state left with sticky
+// handles, for levels whose cascades move more than five handles, and for batches created without the table.
 template <bool TAPE, int NI>
 __device__ __forceinline__ void set_val(Env<NI> &e, const LevelBlob &L, int o0, bool v0) {
+    if (L.closure != nullptr && e.sticky == 0u) {
+        const uint32_t ent = __ldg(L.closure + ((((uint32_t)o0 * 2u + (v0 ? 1u : 0u)) << CLOSURE_BITS) | ((e.flags >> F_DOORS) & ((1u << CLOSURE_BITS) - 1u))));
+        const uint32_t ne = (ent >> CLOSURE_BITS) & 7u;
+        if (ne != 7u) {
+            e.flags = (e.flags & ~(((1u << CLOSURE_BITS) - 1u) << F_DOORS)) | ((ent & ((1u << CLOSURE_BITS) - 1u)) << F_DOORS);
+            for (uint32_t k = 0; k < ne; k++) {
+                const uint32_t ev = ent >> (16u + 3u * k);
+                e.angles[(int64_t)(ev & 3u) * e.n] = handle_angle(((ev >> 2) & 1u) != 0u, draw<TAPE>(e));
+            }
+            return;
+        }
+    }
     if (apply_val<TAPE>(e, L, o0, v0)) trigger_dfs<TAPE>(e, L, o0, v0);
 }
 

@@ -1,5 +1,6 @@
 // Internal POD shared by host (level compiler in tg_capi.cu) and device code.
 #pragma once
+#include <cstddef>
 #include <stdint.h>
 #include <vector_types.h>
 #include "../../include/treasure_b200.h"
@@ -56,7 +57,10 @@ struct alignas(16) LevelBlob {
     uint8_t trig_begin[2 * TG_MAX_OBJECTS + 8];
     uint8_t trig_list[TG_MAX_TRIGGERS];
     float inv_w, inv_h;                  // unused by parity paths (obs divides in double)
-    uint32_t pad_[2];
+    // closure of set_val + process_trigger (objs:76-94, :145-149) for an env without sticky handles, in GLOBAL memory (or
+    // NULL): entry [(2 o + v) << 13 | door / handle / bolt bits] = new bits | events << 13 | (handle | value << 2) << (16 + 3 k)
+    // for the k-th handle whose angle is redrawn, in the walk's order; events == 7: not tabulated, walk the graph
+    const uint32_t *closure;
     // observation program (impl:368-378): obs slot k = OP_* << 4 | index (handle / bolt / item number)
     uint8_t obs_prog[32];
     // row bit masks over the padded columns (bit = column index + PAD), door cells cleared:
@@ -70,6 +74,8 @@ struct alignas(16) LevelBlob {
     uint32_t door_lut[TG_MAX_DOORS][64]; // [rows with doors][closed-door bits] -> column bits of the closed doors of the row
 };
 static_assert(sizeof(LevelBlob) % 16 == 0, "LevelBlob must be a multiple of 16 bytes");
+static_assert(offsetof(LevelBlob, closure) % 8 == 0, "LevelBlob::closure must be 8-byte aligned");
+constexpr int CLOSURE_BITS = TG_MAX_DOORS + TG_MAX_HANDLES + TG_MAX_BOLTS;   // 13: the flag bits from F_DOORS up
 
 // observation program opcodes and the quotient tables behind OP_PX .. OP_IY: lut[0][v + S] = float(v / W) and
 // lut[1][v + S] = float(v / H) for v in [-S, OBS_LUT_N - S), one pair of tables per level (BatchView::obs_lut)
