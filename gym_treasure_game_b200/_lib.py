@@ -81,6 +81,7 @@ _SIGNATURES = {
     "tg_stats_clear": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tg_launch_count": (C.c_int64, [C.c_void_p]),
     "tg_host_traffic": (None, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "tg_debug_level_closure": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(C.c_uint32)]),
     "tg_debug_host_times": (None, [C.c_void_p, C.POINTER(C.c_double)]),
     "tg_debug_phase_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tg_debug_set_step_tile": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -418,7 +418,7 @@ extern "C" int tg_create(const tg_level *const *levels, int32_t n_levels, const 
 
     LevelBlob *d_levels = nullptr;
     CUE(dev_alloc(e, &d_levels, (size_t)n_levels));
-    static const bool no_closure = getenv("TG_NO_CLOSURE") != nullptr;     // debug: every interact walks the trigger graph
+    const bool no_closure = getenv("TG_NO_CLOSURE") != nullptr;            // debug / tests: every interact walks the trigger graph
     for (int l = 0; l < n_levels; l++) {
         LevelBlob blob = levels[l]->blob;
         if (!levels[l]->closure.empty() && !no_closure) {               // the trigger closure lives in global memory, the blob points to it
@@ -763,6 +763,13 @@ extern "C" int tg_step_host_sparse(tg_env *env, const int32_t *actions, float *o
                                    uint8_t *ran, void *stream) {
     const int rc = tg_step_host_sparse_begin(env, actions, obs, reward, done, ran, stream);
     return rc != TG_OK ? rc : tg_step_host_sparse_end(env);
+}
+
+extern "C" int tg_debug_level_closure(const tg_level *lv, int32_t obj, int32_t value, uint32_t bits, uint32_t *entry) {
+    if (!lv || !entry) return fail(TG_ERR_ARG, "null argument");
+    if (obj < 0 || obj >= lv->blob.n_objs || bits >= (1u << CLOSURE_BITS) || lv->closure.empty()) return fail(TG_ERR_ARG, "closure index outside the table");
+    *entry = lv->closure[(((size_t)obj * 2 + (value ? 1 : 0)) << CLOSURE_BITS) | bits];
+    return TG_OK;
 }
 
 extern "C" void tg_debug_host_times(tg_env *env, double *out3) {

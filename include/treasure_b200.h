@@ -189,6 +189,12 @@ int tg_step_host_sparse_end(tg_env *env);
  * last call of this function (then reset).  out3 HOST double[3]. */
 void tg_debug_host_times(tg_env *env, double *out3);
 
+/* Debug / tests: one entry of a level's trigger closure table (the tabulated form of set_val + process_trigger,
+ * objects.py:76-94, :145-149).  obj = object index in file order, value = the value it is set to, bits = door bits (6) |
+ * handle bits << 6 (4) | bolt bits << 10 (3) before the call.  *entry = bits afterwards | events << 13 | (handle index |
+ * value << 2) << (16 + 3 k) for the k-th handle whose angle is redrawn; events == 7: not tabulated.  Needs no device. */
+int tg_debug_level_closure(const tg_level *level, int32_t obj, int32_t value, uint32_t bits, uint32_t *entry);
+
 /* TreasureGame.available_mask (treasure_game.py:83-89).  mask DEV [N][9] u8. */
 int tg_available_mask(tg_env *env, uint8_t *mask, void *stream);
 

@@ -127,3 +127,34 @@ def test_cuda_vs_c_oracle_random_levels():
         assert_state_equal(env, cb, "level %d final" % seed)
         assert list(env.stats().values()) == cb.stats().tolist()
         env.close()
+
+
+@pytest.mark.gpu
+def test_cuda_graph_walk_equals_closure_table(monkeypatch):
+    """The INTERACT tick reads the trigger closure table; batches created with TG_NO_CLOSURE walk the trigger graph on the
+    device instead (the path kept for sticky handles and untabulated cascades).  Both must give the oracle's results."""
+    import torch
+    from gpu_util import assert_state_equal, product_level
+    from gym_treasure_game_b200 import VectorTreasureGame
+    g = torch.Generator().manual_seed(5)
+    for seed in [s for s in SEEDS if random_level(s).triggers][:6]:
+        lv = random_level(seed)
+        n = 512
+        monkeypatch.setenv("TG_NO_CLOSURE", "1")
+        walk = VectorTreasureGame(n, seed=seed, max_episode_steps=40, auto_reset=True, levels=[product_level(lv)], render=False)
+        monkeypatch.delenv("TG_NO_CLOSURE")
+        table = VectorTreasureGame(n, seed=seed, max_episode_steps=40, auto_reset=True, levels=[product_level(lv)], render=False)
+        cb = c_oracle.CBatch(c_oracle.CLevel(lv), n, first_env_id=0, seed=seed, max_episode_steps=40, auto_reset=True)
+        cb.reset()
+        for t in range(80):
+            m = torch.from_numpy(cb.mask().astype(np.float32))
+            m[:, 4] *= 6.0                               # interact whenever it can run, mostly
+            a = torch.multinomial(m + 0.02, 1, generator=g).squeeze(1).to(torch.int32)
+            outs = [e.step_raw(a.cuda()) for e in (walk, table)]
+            o2, r2, d2, ran2, _ = cb.step(a.numpy())
+            for e, (obs, rew, done, ran) in zip((walk, table), outs):
+                np.testing.assert_array_equal(obs.cpu().numpy(), o2.astype(np.float32), err_msg="obs level %d step %d" % (seed, t))
+                np.testing.assert_array_equal(rew.cpu().numpy(), r2); np.testing.assert_array_equal(done.cpu().numpy(), d2)
+        assert_state_equal(walk, cb, "graph walk, level %d" % seed)
+        assert_state_equal(table, cb, "closure table, level %d" % seed)
+        walk.close(); table.close()
