@@ -713,9 +713,50 @@ __device__ __forceinline__ int move_until_aligned(Env<NI> &e, const LevelBlob &L
     while (abs(tpx - e.px) >= 4) {
         const int x = e.px, y = e.py;
         // every cell this tick can look at (x - 20 .. x + 20 after the move, y - 4 .. y + 54 after a 4-px fall) is in the window
-        if (pad_cell(x - 20) < c0 || pad_cell(x + 20) > c0 + 7 || pad_cell(y - 4) < r0 || pad_cell(y + 54) > r0 + 7) return -1;
+        // pad_cell(x - 20) >= c0 && pad_cell(x + 20) <= c0 + 7  <=>  48 c0 - 124 <= x <= 48 c0 + 219; the rows likewise
+        if ((unsigned)(x - (S * c0 - 124)) > 343u || (unsigned)(y - (S * r0 - 140)) > 325u) return -1;
         const bool blocked = (bit(ws, x + 16 * s, y + 4) | bit(ws, x + 16 * s, y + 44)) != 0u;
         const bool cf = can_fall_w(x, y);
+        // Blocked in mid-air (the wall of the ledge a jump is rising along, the wall a drop falls along): the policy keeps
+        // asking for the same side, the side probe keeps failing -- no move, no draw, facing unchanged (impl:305-313) -- and
+        // the tick is its vertical half alone (impl:331-348) with playerx fixed.  Every probe then looks at fixed window
+        // columns: their 8-bit column profiles (bit r = window row r) turn the ticks into a register loop, until the side
+        // probe clears, the player lands, or the window ends (the general form above takes over from the same state).
+        if (blocked && cf) {
+            bool near_item = false;
+#pragma unroll
+            for (int i = 0; i < NI; i++) near_item |= (i < L.n_items) && abs(x - (e.ix[i] + S / 2)) < 24;
+            if (!near_item) {
+                auto colprof = [&](uint64_t w, int xx) -> uint32_t {
+                    return (uint32_t)((((w >> (pad_cell(xx) - c0)) & 0x0101010101010101ull) * 0x0102040810204080ull) >> 56);
+                };
+                const uint32_t pS = colprof(ws, x + 16 * s), pN = colprof(wn, x - 10) | colprof(wn, x + 10),
+                               pU = colprof(wn, x - 4) | colprof(wn, x + 4);
+                auto row = [&](int v) { return pad_cell(v) - r0; };
+                int yy = y, tk = ticker(e.flags), ticks = 0;
+                for (;;) {
+                    ticks++;                                                         // a tick that starts blocked and able to fall
+                    if (tk > 0) {                                                    // impl:331-334
+                        if ((((pU >> row(yy - 4)) | (pU >> row(yy - 1))) & 1u) == 0u) yy -= 4;
+                        tk--;
+                    } else {                                                         // impl:335-346: one pixel at a time, at most 4
+                        int yd = 4;
+                        do {
+                            yy++; yd--;
+                            if ((((pN >> row(yy)) | (pN >> row(yy + 50))) & 1u) != 0u) yd = 0;
+                        } while (yd > 0);
+                    }
+                    if (n + ticks >= TG_TICK_CAP) break;
+                    if ((unsigned)(yy - (S * r0 - 140)) > 325u) break;               // the next tick may look outside the window
+                    if ((((pS >> row(yy + 4)) | (pS >> row(yy + 44))) & 1u) == 0u) break;    // side probe clear
+                    if ((((pN >> row(yy)) | (pN >> row(yy + 50))) & 1u) != 0u) break;        // landed
+                }
+                e.py = yy; e.flags = set_ticker(e.flags, tk);
+                e.total_actions += ticks; n += ticks;
+                if (n >= TG_TICK_CAP) return 0;
+                continue;
+            }
+        }
         int dir = s;
         if (jump && blocked && !cf) dir = -s;
         const bool go = (dir == s) ? !blocked : (bit(ws, x + 16 * dir, y + 4) | bit(ws, x + 16 * dir, y + 44)) == 0u;
@@ -959,8 +1000,25 @@ __device__ __forceinline__ int run_option_to_end(Env<NI> &e, const LevelBlob &L,
                 done = true;
                 break;
             }
-            int room = up ? min(min(min(mod48(py - 4), mod48(py)), min(mod48(py + 44), mod48(py + 50))), py - 2)
+            int room = up ? min(min(mod48(py - 4), mod48(py)), min(mod48(py + 44), mod48(py + 50)))
                           : 47 - max(max(mod48(py), mod48(py + 50)), mod48(py + 51));
+            {   // A longer stretch that is still safe: while the row of py itself holds a ladder cell (probe, impl:240-257) and
+                // something that is not OPEN (no fall, impl:283-288) in the probed columns, neither predicate can change --
+                // whatever the other probed rows enter.  `run` = the padded rows with both, contiguous from the row of py.
+                const uint32_t both = lad & blk;
+                if ((both >> r1) & 1u) {
+                    if (up) {
+                        const uint32_t gap = ~both & ((1u << r1) - 1u);                       // rows below index r1 without
+                        const int r_top = gap ? 32 - __clz(gap) : 0;
+                        room = max(room, py - S * (r_top - PAD));
+                    } else {
+                        const uint32_t gap = ~both & ~((2u << r1) - 1u);                      // rows above index r1 without
+                        const int r_bot = gap ? __ffs(gap) - 2 : TSTRIDE - 1;
+                        room = max(room, S * (r_bot - PAD) + S - 1 - py);
+                    }
+                }
+            }
+            if (up) room = min(room, py - 2);
             if (!TAPE && !near_item) {
                 // (1) four ticks all start inside the stretch when 12 px further on one still does
                 while (room >= 12 && ((e.draws - e.d0) & 3u) == 0u && n <= TG_TICK_CAP - 4) {
@@ -1183,10 +1241,14 @@ __device__ __forceinline__ float obs_quot(const float *__restrict__ lut, int v, 
 // Writes the row to `o` and, when given, to `o2` (the sparse record of tg_step_host_sparse): every value is computed once.
 template <int NI>
 __device__ __forceinline__ void write_obs(const Env<NI> &e, const LevelBlob &L, const float *__restrict__ lut,
-                                          float *__restrict__ o, int obs_dim, float *__restrict__ o2 = nullptr) {
+                                          float *__restrict__ o, int obs_dim, float *__restrict__ o2 = nullptr, bool full = true) {
     const int W = L.cw * S, H = L.ch * S;
     const int nk = L.obs_dim;
     auto put = [&](int k, float v) { if (o) o[k] = v; if (o2) o2[k] = v; };
+    if (!full) {                     // only the player moved (the row holds the env's previous observation): slots 0, 1 (impl:370-371)
+        put(0, obs_quot(lut, e.px, W)); put(1, obs_quot(lut + OBS_LUT_N, e.py, H));
+        return;
+    }
     if (L.obs_prog[31] == 1) {       // the shipped layout's slot order (two handles, key, bolt, gold): straight-line code
         const float *lx = lut, *ly = lut + OBS_LUT_N;
         const double a0 = e.angles[0], a1 = e.angles[e.n];

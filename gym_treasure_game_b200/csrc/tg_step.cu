@@ -208,7 +208,10 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, int cap, const int
                 cd |= (run ? bucket : 255u) << (8 * u);
                 if (run) rank[el0 + u] = (uint16_t)atomicAdd(&hist[bucket], 1);
                 special |= (d ? 1u : 0u) << u;
-                special |= ((!run && ((a == (uint32_t)TG_DOWN_LEFT && ((lo >> PL_ERR_DL) & 1u)) || (a == (uint32_t)TG_DOWN_RIGHT && ((lo >> PL_ERR_DR) & 1u)))) ? 16u : 0u) << u;
+                // "the reference would raise": plan bit PL_ERR_DL + (a - TG_DOWN_LEFT), for the two drop options only (the plan never
+                // sets it together with the option's can_run bit, compute_plan)
+                static_assert(PL_ERR_DR == PL_ERR_DL + 1 && TG_DOWN_RIGHT == TG_DOWN_LEFT + 1, "error bits follow the option ids");
+                special |= ((lo >> (a + (uint32_t)(PL_ERR_DL - TG_DOWN_LEFT))) & (((3u << TG_DOWN_LEFT) >> a) & 1u)) << (4 + u);
             }
             *reinterpret_cast<uint32_t *>(code + el0) = cd;            // el0 is a multiple of 4, cap a multiple of 16
             if (special) {                                             // rare: episode over (time limit / done), or the reference would raise
@@ -263,7 +266,11 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, int cap, const int
     __syncthreads();
     for (int el = tid; el < count; el += STEP_THREADS) {
         const int c = code[el];
-        if (c != 255) perm[hist[c] + rank[el]] = (uint16_t)el;
+        if (c != 255) {
+            perm[hist[c] + rank[el]] = (uint16_t)el;
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(B.core + base + el));     // phase B loads these two records (one
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(B.acct + base + el));     // sector each) at the head of its chunk
+        }
     }
     const int n_run = hist[NBUCKET - 1];                    // exclusive scan: start of the (unused) last bucket = runnable envs
     const int n_idle_rst = n_reset;                         // idle envs to reset; the option lanes append theirs
@@ -329,7 +336,7 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, int cap, const int
         if (valid) {
             load_env(e, B, i, acct);
             if (a == TG_INTERACT) e.d0 = e.draws - drawn_i;
-            else { bool err; option_setup(e, L, a, tcx, err); err0 = e.flags & (1u << F_ERROR); }   // runnable (the plan says so): target column
+            else { bool err; option_setup(e, L, a, tcx, err); err0 = e.flags; }   // runnable (the plan says so): target column; flags before the option
         }
         unsigned long long chunk_t1 = 0, chunk_t2 = 0, chunk_t3 = 0;
         if (B.phase_ts && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(chunk_t1) : "r"(tcx + (int)acct.x) : "memory");
@@ -337,7 +344,7 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, int cap, const int
         if (B.phase_ts && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(chunk_t2) : "r"(n) : "memory");
         if (!valid) continue;
         if (a == TG_INTERACT) n = 1;
-        else newerr = ((e.flags & (1u << F_ERROR)) && !err0) ? 1u : 0u;
+        else newerr = (e.flags & ~err0 & (1u << F_ERROR)) ? 1u : 0u;
         st_cnt += newerr + (1u << 24);
         st_ticks += n;
         const bool jump = a >= TG_JUMP_LEFT;
@@ -360,8 +367,11 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, int cap, const int
             uint32_t *rec = B.sp_count ? B.sp_recs + (size_t)(rec_base + (uint32_t)j) * B.sp_words : nullptr;
             if (rec) { rec[0] = (uint32_t)i; rec[1] = __float_as_uint((float)r); rec[2] = d | 256u; }
             if (obs || rec)
+                // An option other than interact that picked nothing up moved the player and nothing else: two slots of the
+                // row (it holds the env's previous observation, tg_step in treasure_b200.h).  Records carry whole rows.
                 write_obs(e, L, B.obs_lut + (size_t)lid * 2 * OBS_LUT_N, obs ? obs + i * od : nullptr, od,
-                          rec ? reinterpret_cast<float *>(rec + 3) : nullptr);
+                          rec ? reinterpret_cast<float *>(rec + 3) : nullptr,
+                          rec || a == TG_INTERACT || (((e.flags ^ err0) >> F_ERROR) | ((e.flags >> F_ERROR) & 1u)) != 0u);
             if (avail_out) avail_out[i] = (uint16_t)(plan & 0x1FFu);
         }
         if (reward) reward[i] = (float)r;

@@ -145,8 +145,9 @@ int tg_reset(tg_env *env, const uint8_t *mask, float *obs, void *stream);
  * observation of the new episode.
  * Observation rows: an option that cannot run leaves its env untouched (_option.py:22-23), so its row does not
  * change.  When `obs` is the buffer registered with tg_bind_obs and it was the `obs` argument of the previous
- * state-changing call on this env (tg_step / tg_reset / tg_primitive_step), only the rows of envs that ran or were
- * reset are written -- one kernel launch.  Any other `obs` has every row written (a second launch). */
+ * state-changing call on this env (tg_step / tg_reset / tg_primitive_step), only what changed is written -- the two
+ * player slots of an env whose option moved the player and nothing else, the whole row of an env that interacted,
+ * picked something up or was reset -- in one kernel launch.  Any other `obs` has every row written (a second launch). */
 int tg_step(tg_env *env, const int32_t *actions, float *obs, float *reward, uint8_t *done,
             uint8_t *ran, uint16_t *avail, void *stream);
 
