@@ -1000,31 +1000,6 @@ __device__ __forceinline__ int run_option_to_end(Env<NI> &e, const LevelBlob &L,
                 done = true;
                 break;
             }
-#ifdef TG_EXP_LADRUN2
-            // The stretch inside which ticks run unchecked: the ladder probe (impl:240-257) holds while ONE of its probed pixel
-            // rows stays inside a run of ladder rows of the probed columns, the player cannot fall (impl:283-288) while one of
-            // that probe's pixel rows stays inside a run of rows that are not OPEN; a pixel row v going up can move
-            // v - (top pixel of its run) pixels, going down (bottom pixel of its run) - v.  Both predicates hold here, so at
-            // least one term of each is >= 0.
-            int room;
-            if (up) {
-                auto reach = [&](uint32_t m, int v) -> int {
-                    const int r = pad_cell(v);
-                    if (!((m >> r) & 1u)) return -1;
-                    const uint32_t gap = ~m & ((1u << r) - 1u);                               // rows below index r without
-                    return v - S * ((gap ? 32 - __clz(gap) : 0) - PAD);
-                };
-                room = min(max(max(reach(lad, py - 4), reach(lad, py)), reach(lad, py + 44)), max(reach(blk, py), reach(blk, py + 50)));
-            } else {
-                auto reach = [&](uint32_t m, int v) -> int {
-                    const int r = pad_cell(v);
-                    if (!((m >> r) & 1u)) return -1;
-                    const uint32_t gap = ~m & ~((2u << r) - 1u);                              // rows above index r without
-                    return S * ((gap ? __ffs(gap) - 2 : TSTRIDE - 1) - PAD) + S - 1 - v;
-                };
-                room = min(max(reach(lad, py), reach(lad, py + 51)), max(reach(blk, py), reach(blk, py + 50)));
-            }
-#else
             int room = up ? min(min(mod48(py - 4), mod48(py)), min(mod48(py + 44), mod48(py + 50)))
                           : 47 - max(max(mod48(py), mod48(py + 50)), mod48(py + 51));
             {   // A longer stretch that is still safe: while the row of py itself holds a ladder cell (probe, impl:240-257) and
@@ -1043,7 +1018,6 @@ __device__ __forceinline__ int run_option_to_end(Env<NI> &e, const LevelBlob &L,
                     }
                 }
             }
-#endif
             if (up) room = min(room, py - 2);
             if (!TAPE && !near_item) {
                 // (1) four ticks all start inside the stretch when 12 px further on one still does

@@ -172,9 +172,7 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, int cap, const int
                         (!done_out || (reinterpret_cast<uintptr_t>(done_out + base) & 3u) == 0) &&
                         (!ran_out || (reinterpret_cast<uintptr_t>(ran_out + base) & 3u) == 0) &&
                         (!avail_out || (reinterpret_cast<uintptr_t>(avail_out + base) & 7u) == 0);
-#ifdef TG_EXP_PA2
         const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(hist), rank_s = (uint32_t)__cvta_generic_to_shared(rank);
-#endif
         for (int el0 = 4 * tid; el0 < count; el0 += 4 * STEP_THREADS) {
             const int m = min(4, count - el0);
             const int64_t i0 = base + el0;
@@ -206,7 +204,6 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, int cap, const int
                 const uint32_t lenc = ((a < 4u ? lo >> (PL_LEN + 4u * a) : phi[u] >> (4u * a - 16u)) & 15u);
                 const uint32_t bucket = (uint32_t)((0x332241100ull >> (4u * a)) & 15ull) * 12u + 11u - lenc;
                 const uint32_t steps = t_now + 1u - ev[u];
-#ifdef TG_EXP_PA2
                 // branch-free: a warp's lanes disagree on `run` in nearly every element (20 % run), and a branch here costs both of
                 // its sides plus the reconvergence for all of them; the rank is a predicated shared-memory atomic
                 const uint32_t d = (run ? 0u : 0xFFu) & (((lo >> PL_TERM) & 1u) | (steps >= max_steps ? (uint32_t)TG_DONE_TRUNCATED : 0u));
@@ -214,12 +211,6 @@ tg_step_kernel(const __grid_constant__ BatchView B, int tile, int cap, const int
                 cd |= (run ? bucket : 255u) << (8 * u);
                 asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 r;\n\tsetp.ne.u32 p, %0, 0;\n\t@p atom.shared.add.u32 r, [%1], 1;\n\t@p st.shared.u16 [%2], r;\n\t}"
                              :: "r"((uint32_t)run), "r"(hist_s + 4u * bucket), "r"(rank_s + 2u * (uint32_t)(el0 + u)) : "memory");
-#else
-                const uint32_t d = run ? 0u : (((lo >> PL_TERM) & 1u) | (steps >= max_steps ? (uint32_t)TG_DONE_TRUNCATED : 0u));
-                dn |= d << (8 * u);
-                cd |= (run ? bucket : 255u) << (8 * u);
-                if (run) rank[el0 + u] = (uint16_t)atomicAdd(&hist[bucket], 1);
-#endif
                 special |= (d ? 1u : 0u) << u;
                 // "the reference would raise": plan bit PL_ERR_DL + (a - TG_DOWN_LEFT), for the two drop options only (the plan never
                 // sets it together with the option's can_run bit, compute_plan)

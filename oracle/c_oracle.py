@@ -48,6 +48,7 @@ def lib():
         L.tgo_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.tgo_batch_init_with_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.tgo_batch_get_pt.argtypes = [C.c_void_p, C.c_void_p]
+        L.tgo_batch_set_draws.argtypes = [C.c_void_p, C.c_void_p]
         L.tgo_batch_prim_step.argtypes = [C.c_void_p] * 5
         _lib = L
     return _lib
@@ -142,6 +143,11 @@ class CBatch:
         st = np.ascontiguousarray(states, dtype=np.float64).reshape(self.n, self.level.obs_dim)
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         lib().tgo_batch_init_with_state(self.h, _p(st), _p(m))
+
+    def set_draws(self, draws):
+        """Test hook: every env's 32-bit draw index (the counter its Philox blocks are numbered from)."""
+        d = np.ascontiguousarray(draws, dtype=np.uint32).reshape(self.n)
+        lib().tgo_batch_set_draws(self.h, _p(d))
 
     def handles_pt(self):
         pt = np.zeros((self.n, max(self.level.nh, 1)), dtype=np.uint8)

@@ -649,6 +649,14 @@ void tgo_batch_mask(void *bp, uint8_t *mask)               /* tg:83-89 */
 
 void tgo_batch_stats(void *bp, int64_t *out8) { memcpy(out8, ((batch_t *)bp)->stats, 64); }
 
+/* Test hook: the per-env draw index (the 32-bit counter the Philox blocks are numbered from), e.g. to start a
+ * batch just below 2^32 and compare the wrap with the CUDA library ("RNG"). */
+void tgo_batch_set_draws(void *bp, const uint32_t *draws)
+{
+    batch_t *b = bp;
+    for (int64_t i = 0; i < b->n; i++) { b->e[i].draws = draws[i]; b->e[i].d0 = draws[i]; }
+}
+
 /* Flat state dump for differential tests.  Any pointer may be NULL.
  * pos[N*2]=px,py; misc[N*4]=facing,ticker,total_actions,draws; doors/handles/bolts[N*count] 0/1;
  * angles[N*nh]; items[N*ni*4]=x,y,cx,cy; bag[N*4] item index per bag slot or -1 (an item can appear twice);

@@ -305,3 +305,32 @@ def test_philox_mode_statistics(VTG):
     flipped = (h0 != h1).any(axis=1)[m]
     assert abs(flipped.mean() - 0.8) < 6 * np.sqrt(0.8 * 0.2 / m.sum())
     env.close()
+
+
+def test_draw_index_wraps_like_the_oracle():
+    """The per-env draw index is 32 bits wide (RNG): envs started a few draws below 2^32 wrap
+    inside the run, and CUDA and the C oracle must keep agreeing draw for draw through the wrap (outputs every
+    step, full state at the end; Philox mode, auto-reset on)."""
+    from gym_treasure_game_b200 import VectorTreasureGame
+    n = 2048
+    env = VectorTreasureGame(n, seed=99, max_episode_steps=40, auto_reset=True, render=False)
+    cb = c_oracle.CBatch(c_oracle.CLevel(po.default_level()), n, seed=99, max_episode_steps=40, auto_reset=True)
+    cb.reset()
+    start = (0xFFFFFFFF - np.arange(n, dtype=np.int64) % 257).astype(np.uint32)      # 0 .. 256 draws before the wrap
+    st = env.get_state()
+    st["misc"][:, 3] = torch.from_numpy(start.view(np.int32)).to(st["misc"].device)
+    env.set_state(st)
+    cb.set_draws(start)
+    assert_state_equal(env, cb, "after moving the draw index")
+    g = torch.Generator().manual_seed(4)
+    for t in range(90):
+        if t % 3 == 2:                                                              # runnable options: draws get consumed
+            m = torch.from_numpy(cb.mask().astype(np.float32)) + 1e-6
+            a = torch.multinomial(m, 1, generator=g).squeeze(1).to(torch.int32)
+        else:
+            a = torch.randint(0, 9, (n,), generator=g, dtype=torch.int32)
+        assert_step_equal(env.step_raw(a.cuda()), cb.step(a.numpy()), "step %d" % t)
+    assert_state_equal(env, cb, "after the wrap")
+    wrapped = env.get_state()["misc"][:, 3].cpu().numpy().view(np.uint32)
+    assert (wrapped < 0x80000000).all(), "every env should have passed 2^32 draws"
+    env.close()
