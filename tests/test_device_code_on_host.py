@@ -1,0 +1,153 @@
+"""CPU: the CUDA device functions themselves -- csrc/tg_device.cuh: run_option_to_end with its straight-line walker /
+ladder loops, the register-window drop / jump ticks and their blocked-mid-air loop, the closed-form fall, the
+INTERACT tick (closure table and graph walk), compute_plan, reset_env, write_obs with its two-slot rows -- compiled for
+the host by g++ (tests/hostdev/hostdev.cpp: intrinsic shims + a serial driver that mirrors what the step kernel does
+for one env) and compared step by step with the C oracle in Philox mode: observation, reward, done, ran, primitive
+ticks, available mask, error flag and draw index of every env.  The level blob is the one the product library compiles
+(tg_level_create is host code), so no GPU is needed.  This is test infrastructure: nothing here is a CPU path of the
+product (the library still refuses to run without a device, tests/test_library_abi.py::test_no_cpu_fallback).
+Reference behaviour: treasure_game.py:91-96, _option.py:20-36, _move_options.py, _treasure_game_impl.py:290-359."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import c_oracle
+import py_oracle as po
+from level_fuzz import random_level, usable
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hostdev", "hostdev.cpp")
+OUT = os.path.join(HERE, "hostdev", "_build", "libhostdev.so")
+CSRC = os.path.join(os.path.dirname(HERE), "gym_treasure_game_b200", "csrc")
+CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+
+
+def _build():
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("tg_device.cuh", "tg_types.h")]
+    if os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
+        return OUT
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
+                           "-I", CUDA_INC, "-o", OUT, SRC])
+    return OUT
+
+
+@pytest.fixture(scope="module")
+def hostdev():
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    L = C.CDLL(_build())
+    L.hostdev_blob_size.restype = C.c_size_t
+    L.hostdev_create.restype = C.c_void_p
+    L.hostdev_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.hostdev_destroy.argtypes = [C.c_void_p]
+    L.hostdev_reset.argtypes = [C.c_void_p, C.c_void_p]
+    L.hostdev_step.argtypes = [C.c_void_p] * 7
+    L.hostdev_mask.argtypes = [C.c_void_p, C.c_void_p]
+    L.hostdev_flags.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _compiled(lvt):
+    from gpu_util import product_level
+    from gym_treasure_game_b200.vector_env import CompiledLevel
+    return CompiledLevel(product_level(lvt), with_sprites=False)
+
+
+def _closure_table(cl, n_objs):
+    """The level's closure table, entry by entry through the library's debug accessor."""
+    from gym_treasure_game_b200 import _lib
+    L = _lib.lib()
+    tab = np.zeros((n_objs * 2) << 13, dtype=np.uint32)
+    ent = C.c_uint32()
+    for o in range(n_objs):
+        for v in (0, 1):
+            base = ((o * 2 + v) << 13)
+            for bits in range(1 << 13):
+                _lib.check(L.tg_debug_level_closure(cl.handle, o, v, bits, C.byref(ent)))
+                tab[base | bits] = ent.value
+    return tab
+
+
+def _levels():
+    yield "default", po.default_level()
+    yield "mirrored", po.mirrored_level(po.default_level())
+    k = 0
+    for s in range(80):
+        lv = random_level(s)
+        if usable(lv):
+            yield "fuzz%d" % s, lv
+            k += 1
+            if k >= 10:
+                break
+
+
+def _run(hostdev, lvt, n, steps, seed, max_steps, with_closure, first_env_id=0):
+    cl = _compiled(lvt)
+    size = hostdev.hostdev_blob_size()
+    blob = C.string_at(cl.handle, size)            # tg_level begins with its LevelBlob (csrc/tg_capi.cu)
+    info = cl.info
+    tab = _closure_table(cl, info.n_objects) if with_closure else None
+    h = hostdev.hostdev_create(blob, _ptr(tab) if tab is not None else None, 0 if tab is None else tab.size, n,
+                               first_env_id, seed, max_steps, 1, info.frame_w, info.frame_h)
+    cb = c_oracle.CBatch(c_oracle.CLevel(lvt), n, first_env_id=first_env_id, seed=seed, max_episode_steps=max_steps,
+                         auto_reset=True)
+    try:
+        od = info.obs_dim
+        obs = np.zeros((n, od), np.float32)
+        rew = np.zeros(n, np.float32); done = np.zeros(n, np.uint8); ran = np.zeros(n, np.uint8); ticks = np.zeros(n, np.int32)
+        mask = np.zeros((n, 9), np.uint8); err = np.zeros(n, np.uint8); draws = np.zeros(n, np.uint32)
+        hostdev.hostdev_reset(h, _ptr(obs))
+        o0 = cb.reset()
+        np.testing.assert_array_equal(obs, o0.astype(np.float32), err_msg="obs after reset")
+        rng = np.random.default_rng(seed)
+        ran_total = 0
+        for t in range(steps):
+            m = cb.mask()
+            hostdev.hostdev_mask(h, _ptr(mask))
+            np.testing.assert_array_equal(mask, m, err_msg="available mask before step %d" % t)
+            if t % 3 == 0:                              # the benchmark's law ...
+                a = rng.integers(0, 9, n).astype(np.int32)
+            else:                                       # ... and runnable options, so that episodes get somewhere
+                p = m.astype(np.float64) + 1e-9
+                p /= p.sum(1, keepdims=True)
+                a = (p.cumsum(1) > rng.random((n, 1))).argmax(1).astype(np.int32)
+            if t % 17 == 5:
+                a[::7] = 11                             # invalid ids: treasure_game.py:92 raises; here: not run
+            hostdev.hostdev_step(h, _ptr(a), _ptr(obs), _ptr(rew), _ptr(done), _ptr(ran), _ptr(ticks))
+            o2, r2, d2, ran2, tk2 = cb.step(a)
+            msg = "step %d" % t
+            np.testing.assert_array_equal(ran, ran2, err_msg="ran " + msg)
+            np.testing.assert_array_equal(ticks, tk2, err_msg="primitive ticks " + msg)
+            np.testing.assert_array_equal(rew, r2, err_msg="reward " + msg)
+            np.testing.assert_array_equal(done, d2, err_msg="done " + msg)
+            np.testing.assert_array_equal(obs, o2.astype(np.float32), err_msg="obs " + msg)
+            ran_total += int(ran.sum())
+        st = cb.state()
+        hostdev.hostdev_flags(h, _ptr(err), _ptr(draws))
+        np.testing.assert_array_equal(draws, st["misc"][:, 3].view(np.uint32), err_msg="draw index")
+        np.testing.assert_array_equal(err.astype(np.int64), (st["acct"][:, 2] & 1), err_msg="error flag")
+        return ran_total
+    finally:
+        hostdev.hostdev_destroy(h)
+
+
+@pytest.mark.parametrize("name,lvt", list(_levels()), ids=lambda x: x if isinstance(x, str) else "")
+def test_device_functions_match_c_oracle(hostdev, name, lvt):
+    """Graph-walk INTERACT (no closure table), 384 envs x 150 steps per level, time limit 40 with auto-reset."""
+    ran = _run(hostdev, lvt, n=384, steps=150, seed=1000 + len(name), max_steps=40, with_closure=False, first_env_id=12345)
+    assert ran > 384 * 20
+
+
+def test_device_functions_with_closure_table(hostdev):
+    """The shipped level with the per-level closure table behind INTERACT (what the step kernel reads), 1024 envs."""
+    ran = _run(hostdev, po.default_level(), n=1024, steps=200, seed=7, max_steps=100, with_closure=True)
+    assert ran > 1024 * 40
