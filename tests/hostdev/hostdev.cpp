@@ -47,17 +47,19 @@ struct Batch {
     std::vector<uint2> items23;
     std::vector<double> angles;
     std::vector<float> lut;
+    std::vector<double> tape;          // parity mode (tg_set_draw_tape): recorded reference draws, per env
+    std::vector<int64_t> tape_off;
     uint32_t counter = 0;              // BatchView::step_counter[0]
     BatchView B{};
 };
 
-template <int NI>
+template <bool TAPE, int NI>
 void reset_one(Batch &b, int64_t i, float *obs) {                                   // tg_reset_kernel (mask == NULL)
     const LevelBlob &L = b.level;
     Env<NI> e; uint4 acct;
     load_env(e, b.B, i, acct);
     e.flags &= ~(1u << F_ERROR);
-    reset_env<false>(e, L);
+    reset_env<TAPE>(e, L);
     acct.y = 0;
     store_env(e, b.B, i, acct);
     b.plan[i] = plan_of(e, L);
@@ -66,22 +68,22 @@ void reset_one(Batch &b, int64_t i, float *obs) {                               
 }
 
 // phase C for one env: `drawn` uniforms were consumed by the option that ended the episode in this call (0: idle env)
-template <int NI>
+template <bool TAPE, int NI>
 void reset_in_step(Batch &b, int64_t i, uint32_t drawn, uint32_t t_now, float *obs) {
     const LevelBlob &L = b.level;
     Env<NI> e; uint4 acct;
     load_env(e, b.B, i, acct);
     acct.y = 0; acct.z = 0;
     e.d0 = e.draws - drawn;
-    if (drawn & 3u) { const uint4 o = philox_block(e.d0, drawn >> 2, e.id_lo, e.id_hi, e.key0, e.key1); e.w0 = o.x; e.w1 = o.y; e.w2 = o.z; e.w3 = o.w; }
-    reset_env<false>(e, L);
+    if (!TAPE && (drawn & 3u)) { const uint4 o = philox_block(e.d0, drawn >> 2, e.id_lo, e.id_hi, e.key0, e.key1); e.w0 = o.x; e.w1 = o.y; e.w2 = o.z; e.w3 = o.w; }
+    reset_env<TAPE>(e, L);
     store_env(e, b.B, i, acct);
     b.plan[i] = plan_of(e, L);
     b.ep_start[i] = t_now + 1u;
     if (obs) write_obs(e, L, b.lut.data(), obs + i * b.B.obs_dim, b.B.obs_dim);
 }
 
-template <int NI>
+template <bool TAPE, int NI>
 void step_one(Batch &b, int64_t i, int action, uint32_t t_now, float *obs, float *reward, uint8_t *done, uint8_t *ran, int32_t *ticks) {
     const LevelBlob &L = b.level;
     const BatchView &B = b.B;
@@ -96,7 +98,7 @@ void step_one(Batch &b, int64_t i, int action, uint32_t t_now, float *obs, float
         if ((lo >> (a + (uint32_t)(PL_ERR_DL - TG_DOWN_LEFT))) & (((3u << TG_DOWN_LEFT) >> a) & 1u))
             b.core[i].y |= 1u << F_ERROR;                                            // the reference would raise
         reward[i] = 0.f; done[i] = (uint8_t)d; ran[i] = 0; ticks[i] = 0;
-        if (d && B.auto_reset) reset_in_step<NI>(b, i, 0u, t_now, obs);
+        if (d && B.auto_reset) reset_in_step<TAPE, NI>(b, i, 0u, t_now, obs);
         return;
     }
     Env<NI> e; uint4 acct;
@@ -104,14 +106,14 @@ void step_one(Batch &b, int64_t i, int action, uint32_t t_now, float *obs, float
     int tcx = 0;
     if (a == TG_INTERACT) {                                                         // interact_option_mem
         load_env(e, B, i, acct);
-        tick<false, NI, true>(e, L, A_INTERACT);
+        tick<TAPE, NI, true>(e, L, A_INTERACT);
         store_env(e, B, i, acct);
         drawn_i = e.draws - e.d0;
     }
     load_env(e, B, i, acct);
     if (a == TG_INTERACT) e.d0 = e.draws - drawn_i;
     else { bool err; option_setup(e, L, (int)a, tcx, err); flags0 = e.flags; }
-    int n = run_option_to_end<false, NI, false>(e, L, (int)a, tcx, a != TG_INTERACT);
+    int n = run_option_to_end<TAPE, NI, false>(e, L, (int)a, tcx, a != TG_INTERACT);
     if (a == TG_INTERACT) n = 1;
     const bool jump = a >= TG_JUMP_LEFT;
     const int r = -n - (jump ? 4 : 0);
@@ -121,7 +123,7 @@ void step_one(Batch &b, int64_t i, int action, uint32_t t_now, float *obs, float
     if (d && B.auto_reset) {
         acct.y = 0;
         store_env(e, B, i, acct);
-        reset_in_step<NI>(b, i, min(e.draws - e.d0, 0xFFFFu), t_now, obs);
+        reset_in_step<TAPE, NI>(b, i, min(e.draws - e.d0, 0xFFFFu), t_now, obs);
     } else {
         store_env(e, B, i, acct);
         b.plan[i] = plan_of(e, L);
@@ -167,9 +169,22 @@ void *hostdev_create(const void *blob, const uint32_t *closure, int64_t n_closur
 
 void hostdev_destroy(void *h) { delete static_cast<Batch *>(h); }
 
+// parity mode, like tg_set_draw_tape: env i draws tape[off[i] .. off[i + 1]) instead of Philox words
+void hostdev_set_tape(void *h, const double *tape, const int64_t *off) {
+    Batch &b = *static_cast<Batch *>(h);
+    b.tape_off.assign(off, off + b.n + 1);
+    b.tape.assign(tape, tape + off[b.n]);
+    if (b.tape.empty()) b.tape.push_back(0.0);
+    b.B.tape = b.tape.data(); b.B.tape_off = b.tape_off.data();
+}
+
 void hostdev_reset(void *h, float *obs) {
     Batch &b = *static_cast<Batch *>(h);
-    for (int64_t i = 0; i < b.n; i++) { if (b.ni > 2) reset_one<4>(b, i, obs); else reset_one<2>(b, i, obs); }
+    const bool tape = b.B.tape != nullptr;
+    for (int64_t i = 0; i < b.n; i++) {
+        if (tape) { if (b.ni > 2) reset_one<true, 4>(b, i, obs); else reset_one<true, 2>(b, i, obs); }
+        else { if (b.ni > 2) reset_one<false, 4>(b, i, obs); else reset_one<false, 2>(b, i, obs); }
+    }
 }
 
 // one TreasureGame.step for every env; obs is the caller's persistent [n][obs_dim] buffer (rows are updated in place,
@@ -177,9 +192,15 @@ void hostdev_reset(void *h, float *obs) {
 void hostdev_step(void *h, const int32_t *actions, float *obs, float *reward, uint8_t *done, uint8_t *ran, int32_t *ticks) {
     Batch &b = *static_cast<Batch *>(h);
     const uint32_t t_now = b.counter;
+    const bool tape = b.B.tape != nullptr;
     for (int64_t i = 0; i < b.n; i++) {
-        if (b.ni > 2) step_one<4>(b, i, actions[i], t_now, obs, reward, done, ran, ticks);
-        else step_one<2>(b, i, actions[i], t_now, obs, reward, done, ran, ticks);
+        if (tape) {
+            if (b.ni > 2) step_one<true, 4>(b, i, actions[i], t_now, obs, reward, done, ran, ticks);
+            else step_one<true, 2>(b, i, actions[i], t_now, obs, reward, done, ran, ticks);
+        } else {
+            if (b.ni > 2) step_one<false, 4>(b, i, actions[i], t_now, obs, reward, done, ran, ticks);
+            else step_one<false, 2>(b, i, actions[i], t_now, obs, reward, done, ran, ticks);
+        }
     }
     b.counter = t_now + 1u;
 }

@@ -2,8 +2,9 @@
 ladder loops, the register-window drop / jump ticks and their blocked-mid-air loop, the closed-form fall, the
 INTERACT tick (closure table and graph walk), compute_plan, reset_env, write_obs with its two-slot rows -- compiled for
 the host by g++ (tests/hostdev/hostdev.cpp: intrinsic shims + a serial driver that mirrors what the step kernel does
-for one env) and compared step by step with the C oracle in Philox mode: observation, reward, done, ran, primitive
-ticks, available mask, error flag and draw index of every env.  The level blob is the one the product library compiles
+for one env) and compared step by step (a) with the C oracle in Philox mode: observation, reward, done, ran, primitive
+ticks, available mask, error flag and draw index of every env, and (b) in parity mode with the reference-generated golden
+trajectories, the reference's own draws injected.  The level blob is the one the product library compiles
 (tg_level_create is host code), so no GPU is needed.  This is test infrastructure: nothing here is a CPU path of the
 product (the library still refuses to run without a device, tests/test_library_abi.py::test_no_cpu_fallback).
 Reference behaviour: treasure_game.py:91-96, _option.py:20-36, _move_options.py, _treasure_game_impl.py:290-359."""
@@ -49,6 +50,7 @@ def hostdev():
     L.hostdev_step.argtypes = [C.c_void_p] * 7
     L.hostdev_mask.argtypes = [C.c_void_p, C.c_void_p]
     L.hostdev_flags.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hostdev_set_tape.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -151,3 +153,50 @@ def test_device_functions_with_closure_table(hostdev):
     """The shipped level with the per-level closure table behind INTERACT (what the step kernel reads), 1024 envs."""
     ran = _run(hostdev, po.default_level(), n=1024, steps=200, seed=7, max_steps=100, with_closure=True)
     assert ran > 1024 * 40
+
+
+def _golden_paths():
+    from conftest import golden_files, load_golden
+    return [p for p in golden_files() if not any("restore" in st for st in load_golden(p)["steps"])]
+
+
+@pytest.mark.parametrize("path", _golden_paths(), ids=lambda p: os.path.basename(p)[:-8])
+def test_device_functions_replay_reference_golden(hostdev, path):
+    """The reference-generated golden trajectories (tools/gen_golden.py ran the unmodified reference and recorded its
+    uniform draws) through the host-compiled device code in parity mode: available mask before every step, whether the
+    option ran (the reference's None), reward, primitive ticks, done (treasure_game.py:95), the float32 observation and
+    the number of draws consumed, every step.  (The init_with_state trajectories stay with the -m gpu replay.)"""
+    from conftest import golden_level, load_golden
+    rec = load_golden(path)
+    lvt = golden_level(rec)
+    cl = _compiled(lvt)
+    info = cl.info
+    blob = C.string_at(cl.handle, hostdev.hostdev_blob_size())
+    h = hostdev.hostdev_create(blob, None, 0, 1, 0, 1, 0, 0, info.frame_w, info.frame_h)
+    try:
+        tape = np.asarray(rec["tape"], dtype=np.float64)
+        off = np.array([0, tape.size], dtype=np.int64)
+        hostdev.hostdev_set_tape(h, _ptr(tape), _ptr(off))
+        od = info.obs_dim
+        obs = np.zeros((1, od), np.float32)
+        rew = np.zeros(1, np.float32); done = np.zeros(1, np.uint8); ran = np.zeros(1, np.uint8); ticks = np.zeros(1, np.int32)
+        mask = np.zeros((1, 9), np.uint8); err = np.zeros(1, np.uint8); draws = np.zeros(1, np.uint32)
+        hostdev.hostdev_reset(h, None)                    # the reference constructor's draws
+        hostdev.hostdev_reset(h, _ptr(obs))               # TreasureGame.reset()
+        np.testing.assert_array_equal(obs[0], np.asarray(rec["init"]["obs"], dtype=np.float32))
+        a = np.zeros(1, np.int32)
+        for t, st in enumerate(rec["steps"]):
+            hostdev.hostdev_mask(h, _ptr(mask))
+            assert mask[0].tolist() == st["mask"], t
+            a[0] = st["a"]
+            hostdev.hostdev_step(h, _ptr(a), _ptr(obs), _ptr(rew), _ptr(done), _ptr(ran), _ptr(ticks))
+            assert bool(ran[0]) == (st["r"] is not None), t
+            assert int(rew[0]) == (st["r"] or 0), t
+            if st["r"] is not None and st.get("ticks") is not None:
+                assert int(ticks[0]) == st["ticks"], t
+            assert bool(done[0] & 1) == st["done"], t
+            np.testing.assert_array_equal(obs[0], np.asarray(st["obs"], dtype=np.float32), err_msg=str(t))
+            hostdev.hostdev_flags(h, _ptr(err), _ptr(draws))
+            assert int(draws[0]) == st["draws"] and not err[0], t
+    finally:
+        hostdev.hostdev_destroy(h)
