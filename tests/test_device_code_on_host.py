@@ -25,6 +25,7 @@ SRC = os.path.join(HERE, "hostdev", "hostdev.cpp")
 OUT = os.path.join(HERE, "hostdev", "_build", "libhostdev.so")
 CSRC = os.path.join(os.path.dirname(HERE), "gym_treasure_game_b200", "csrc")
 CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+RARE_WEIGHT = np.array([1, 1, 1, 1, 1, 4, 4, 4, 4], dtype=np.float64)
 
 
 def _build():
@@ -83,12 +84,12 @@ def _levels():
     yield "default", po.default_level()
     yield "mirrored", po.mirrored_level(po.default_level())
     k = 0
-    for s in range(80):
+    for s in range(200):
         lv = random_level(s)
         if usable(lv):
             yield "fuzz%d" % s, lv
             k += 1
-            if k >= 10:
+            if k >= 24:
                 break
 
 
@@ -118,8 +119,8 @@ def _run(hostdev, lvt, n, steps, seed, max_steps, with_closure, first_env_id=0):
             np.testing.assert_array_equal(mask, m, err_msg="available mask before step %d" % t)
             if t % 3 == 0:                              # the benchmark's law ...
                 a = rng.integers(0, 9, n).astype(np.int32)
-            else:                                       # ... and runnable options, so that episodes get somewhere
-                p = m.astype(np.float64) + 1e-9
+            else:                                       # ... and runnable options (drops and jumps four times as likely:
+                p = m.astype(np.float64) * RARE_WEIGHT + 1e-9     # they are 0.04 % of the steps under the benchmark's law)
                 p /= p.sum(1, keepdims=True)
                 a = (p.cumsum(1) > rng.random((n, 1))).argmax(1).astype(np.int32)
             if t % 17 == 5:
