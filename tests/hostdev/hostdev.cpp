@@ -50,6 +50,8 @@ struct Batch {
     std::vector<double> tape;          // parity mode (tg_set_draw_tape): recorded reference draws, per env
     std::vector<int64_t> tape_off;
     uint32_t counter = 0;              // BatchView::step_counter[0]
+    bool obs_stale = false;            // a call changed state without writing rows (the library's obs_sync == NULL): the next
+                                       // step rewrites every row, as tg_obs_kernel does after the step kernel
     BatchView B{};
 };
 
@@ -133,6 +135,45 @@ void step_one(Batch &b, int64_t i, int action, uint32_t t_now, float *obs, float
     reward[i] = (float)r; done[i] = (uint8_t)d; ran[i] = 1; ticks[i] = n;
 }
 
+template <int NI>
+void obs_one(Batch &b, int64_t i, float *obs) {                                     // tg_obs_kernel
+    Env<NI> e; uint4 acct;
+    load_env(e, b.B, i, acct);
+    write_obs(e, b.level, b.lut.data(), obs + i * b.B.obs_dim, b.B.obs_dim);
+}
+
+template <bool TAPE, int NI>
+void init_with_state_one(Batch &b, int64_t i, const double *states) {               // tg_init_with_state_kernel
+    Env<NI> e; uint4 acct;
+    load_env(e, b.B, i, acct);
+    init_with_state_env<TAPE>(e, b.level, states + i * b.B.obs_dim);
+    store_env(e, b.B, i, acct);
+    b.plan[i] = plan_of(e, b.level);
+}
+
+template <bool TAPE, int NI>
+void primitive_one(Batch &b, int64_t i, int a, uint32_t t_now, float *obs, float *reward, uint8_t *done) {   // tg_primitive_kernel
+    const LevelBlob &L = b.level;
+    const BatchView &B = b.B;
+    Env<NI> e; uint4 acct;
+    load_env(e, B, i, acct);
+    tick<TAPE>(e, L, a);
+    const int r = (a == A_JUMP) ? -5 : -1;
+    acct.y = (uint32_t)((int)acct.y + r);
+    const uint32_t steps = t_now + 1u - b.ep_start[i];
+    const bool term = is_done(e, L);
+    const bool trunc = B.max_steps > 0 && steps >= (uint32_t)B.max_steps;
+    const int d = (term ? TG_DONE_TERMINATED : 0) | (trunc ? TG_DONE_TRUNCATED : 0);
+    if (d && B.auto_reset) { reset_env<TAPE>(e, L); acct.y = 0; b.ep_start[i] = t_now + 1u; }
+    store_env(e, B, i, acct);
+    b.plan[i] = plan_of(e, L);
+    if (obs) write_obs(e, L, b.lut.data(), obs + i * B.obs_dim, B.obs_dim);
+    reward[i] = (float)r; done[i] = (uint8_t)d;
+}
+
+template <class F2, class F4>
+void for_each_env(Batch &b, F2 f2, F4 f4) { for (int64_t i = 0; i < b.n; i++) { if (b.ni > 2) f4(i); else f2(i); } }
+
 }  // namespace
 
 extern "C" {
@@ -203,6 +244,48 @@ void hostdev_step(void *h, const int32_t *actions, float *obs, float *reward, ui
         }
     }
     b.counter = t_now + 1u;
+    if (b.obs_stale && obs) { for_each_env(b, [&](int64_t i) { obs_one<2>(b, i, obs); }, [&](int64_t i) { obs_one<4>(b, i, obs); }); b.obs_stale = false; }
+}
+
+// _TreasureGameImpl.init_with_state (impl:447-481) for every env; states [n][obs_dim] float64, -99 keeps the current value
+void hostdev_init_with_state(void *h, const double *states) {
+    Batch &b = *static_cast<Batch *>(h);
+    if (b.B.tape) for_each_env(b, [&](int64_t i) { init_with_state_one<true, 2>(b, i, states); }, [&](int64_t i) { init_with_state_one<true, 4>(b, i, states); });
+    else for_each_env(b, [&](int64_t i) { init_with_state_one<false, 2>(b, i, states); }, [&](int64_t i) { init_with_state_one<false, 4>(b, i, states); });
+    b.obs_stale = true;
+}
+
+// one _TreasureGameImpl.step(action) (impl:290-359) for every env, like tg_primitive_step: every row is written
+void hostdev_primitive_step(void *h, const int32_t *actions, float *obs, float *reward, uint8_t *done) {
+    Batch &b = *static_cast<Batch *>(h);
+    const uint32_t t = b.counter;
+    if (b.B.tape) for_each_env(b, [&](int64_t i) { primitive_one<true, 2>(b, i, actions[i], t, obs, reward, done); }, [&](int64_t i) { primitive_one<true, 4>(b, i, actions[i], t, obs, reward, done); });
+    else for_each_env(b, [&](int64_t i) { primitive_one<false, 2>(b, i, actions[i], t, obs, reward, done); }, [&](int64_t i) { primitive_one<false, 4>(b, i, actions[i], t, obs, reward, done); });
+    b.counter = t + 1u;
+    b.obs_stale = obs == nullptr;
+}
+
+// unpacked state, the layout of tg_get_state (strides TG_MAX_*): pos[n][2], misc[n][4] = facing, ticker, total_actions,
+// draws; doors[n][6], handles[n][4], bolts[n][3] bytes; angles[n][4]; items[n][4][2]; bag[n][4] (-1 = empty); sticky[n]
+void hostdev_state(void *h, int32_t *pos, int32_t *misc, uint8_t *doors, uint8_t *handles, uint8_t *bolts, double *angles,
+                   int32_t *items, int32_t *bag, uint8_t *sticky) {
+    Batch &b = *static_cast<Batch *>(h);
+    for (int64_t i = 0; i < b.n; i++) {
+        const uint4 c = b.core[i], a = b.acct[i];
+        const uint32_t f = c.y;
+        pos[i * 2] = core_px(c.x); pos[i * 2 + 1] = hi16(c.x);
+        misc[i * 4] = f & 1u; misc[i * 4 + 1] = ticker(f); misc[i * 4 + 2] = (int)a.w; misc[i * 4 + 3] = (int)a.x;
+        for (int j = 0; j < TG_MAX_DOORS; j++) doors[i * TG_MAX_DOORS + j] = (f >> (F_DOORS + j)) & 1u;
+        for (int j = 0; j < TG_MAX_HANDLES; j++) handles[i * TG_MAX_HANDLES + j] = (f >> (F_HANDLES + j)) & 1u;
+        for (int j = 0; j < TG_MAX_BOLTS; j++) bolts[i * TG_MAX_BOLTS + j] = (f >> (F_BOLTS + j)) & 1u;
+        for (int j = 0; j < TG_MAX_HANDLES; j++) angles[i * TG_MAX_HANDLES + j] = b.angles[(size_t)j * b.n + i];
+        uint32_t it[4] = {c.z, c.w, 0u, 0u};
+        if (b.ni > 2) { it[2] = b.items23[i].x; it[3] = b.items23[i].y; }
+        for (int j = 0; j < TG_MAX_ITEMS; j++) { items[(i * TG_MAX_ITEMS + j) * 2] = lo16(it[j]); items[(i * TG_MAX_ITEMS + j) * 2 + 1] = hi16(it[j]); }
+        const int len = bag_len(f);
+        for (int j = 0; j < TG_MAX_ITEMS; j++) bag[i * TG_MAX_ITEMS + j] = (j < len) ? (int)((f >> (F_BAGORD + 2 * j)) & 3u) : -1;
+        sticky[i] = (uint8_t)core_sticky(c.x);
+    }
 }
 
 void hostdev_mask(void *h, uint8_t *mask9) {                                         // tg_mask_kernel

@@ -3,8 +3,8 @@ ladder loops, the register-window drop / jump ticks and their blocked-mid-air lo
 INTERACT tick (closure table and graph walk), compute_plan, reset_env, write_obs with its two-slot rows -- compiled for
 the host by g++ (tests/hostdev/hostdev.cpp: intrinsic shims + a serial driver that mirrors what the step kernel does
 for one env) and compared step by step (a) with the C oracle in Philox mode: observation, reward, done, ran, primitive
-ticks, available mask, error flag and draw index of every env, and (b) in parity mode with the reference-generated golden
-trajectories, the reference's own draws injected.  The level blob is the one the product library compiles
+ticks, available mask, full state, error flag and draw index of every env (option steps and primitive ticks), and (b) in
+parity mode with all reference-generated golden trajectories, the reference's own draws injected (init_with_state included).  The level blob is the one the product library compiles
 (tg_level_create is host code), so no GPU is needed.  This is test infrastructure: nothing here is a CPU path of the
 product (the library still refuses to run without a device, tests/test_library_abi.py::test_no_cpu_fallback).
 Reference behaviour: treasure_game.py:91-96, _option.py:20-36, _move_options.py, _treasure_game_impl.py:290-359."""
@@ -52,11 +52,51 @@ def hostdev():
     L.hostdev_mask.argtypes = [C.c_void_p, C.c_void_p]
     L.hostdev_flags.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.hostdev_set_tape.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hostdev_init_with_state.argtypes = [C.c_void_p, C.c_void_p]
+    L.hostdev_primitive_step.argtypes = [C.c_void_p] * 5
+    L.hostdev_state.argtypes = [C.c_void_p] * 10
     return L
 
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def _state(hostdev, h, n):
+    """Unpacked state of every env (the layout of tg_get_state)."""
+    st = dict(pos=np.zeros((n, 2), np.int32), misc=np.zeros((n, 4), np.int32), doors=np.zeros((n, 6), np.uint8),
+              handles=np.zeros((n, 4), np.uint8), bolts=np.zeros((n, 3), np.uint8), angles=np.zeros((n, 4), np.float64),
+              items=np.zeros((n, 4, 2), np.int32), bag=np.zeros((n, 4), np.int32), sticky=np.zeros(n, np.uint8))
+    hostdev.hostdev_state(h, *[_ptr(st[k]) for k in ("pos", "misc", "doors", "handles", "bolts", "angles", "items", "bag", "sticky")])
+    return st
+
+
+def _assert_state_equal(hostdev, h, cb, msg):
+    """Full state against the C oracle batch, bit-exact (what tests/gpu_util.py::assert_state_equal checks on the GPU)."""
+    st, cs, lv = _state(hostdev, h, cb.n), cb.state(), cb.level
+    np.testing.assert_array_equal(st["pos"], cs["pos"], err_msg="pos " + msg)
+    np.testing.assert_array_equal(st["misc"], cs["misc"], err_msg="facing/ticker/total_actions/draws " + msg)
+    np.testing.assert_array_equal(st["doors"][:, : lv.nd], cs["doors"], err_msg="doors " + msg)
+    np.testing.assert_array_equal(st["handles"][:, : lv.nh], cs["handles"], err_msg="handles " + msg)
+    np.testing.assert_array_equal(st["bolts"][:, : lv.nb], cs["bolts"], err_msg="bolts " + msg)
+    np.testing.assert_array_equal(st["angles"][:, : lv.nh], cs["angles"], err_msg="angles (f64 bit-exact) " + msg)
+    np.testing.assert_array_equal(st["items"][:, : lv.ni], cs["items"][:, :, :2], err_msg="items " + msg)
+    np.testing.assert_array_equal(st["bag"], cs["bag"], err_msg="bag " + msg)
+    pt = cb.handles_pt()
+    if lv.nh:
+        np.testing.assert_array_equal(np.stack([(st["sticky"] >> k) & 1 for k in range(lv.nh)], axis=1), pt, err_msg="sticky " + msg)
+
+
+def _snapshot(hostdev, h, info):
+    """Env 0 in the dict layout of the golden records (VectorTreasureGame.snapshot)."""
+    c = {k: v[0] for k, v in _state(hostdev, h, 1).items()}
+    return dict(
+        px=int(c["pos"][0]), py=int(c["pos"][1]), facing=int(c["misc"][0]), ticker=int(c["misc"][1]),
+        doors=[int(v) for v in c["doors"][: info.n_doors]], handles_up=[int(v) for v in c["handles"][: info.n_handles]],
+        angles=[float(v) for v in c["angles"][: info.n_handles]], bolts=[int(v) for v in c["bolts"][: info.n_bolts]],
+        items=[(int(x), int(y), int(np.trunc(x / 48)), int(np.trunc(y / 48))) for x, y in c["items"][: info.n_items]],
+        bag=[int(v) for v in c["bag"] if v >= 0], total_actions=int(c["misc"][2]),
+        handles_pt=[(int(c["sticky"]) >> k) & 1 for k in range(info.n_handles)])
 
 
 def _compiled(lvt):
@@ -134,6 +174,9 @@ def _run(hostdev, lvt, n, steps, seed, max_steps, with_closure, first_env_id=0):
             np.testing.assert_array_equal(done, d2, err_msg="done " + msg)
             np.testing.assert_array_equal(obs, o2.astype(np.float32), err_msg="obs " + msg)
             ran_total += int(ran.sum())
+            if t % 50 == 49:
+                _assert_state_equal(hostdev, h, cb, msg)
+        _assert_state_equal(hostdev, h, cb, "final")
         st = cb.state()
         hostdev.hostdev_flags(h, _ptr(err), _ptr(draws))
         np.testing.assert_array_equal(draws, st["misc"][:, 3].view(np.uint32), err_msg="draw index")
@@ -157,17 +200,18 @@ def test_device_functions_with_closure_table(hostdev):
 
 
 def _golden_paths():
-    from conftest import golden_files, load_golden
-    return [p for p in golden_files() if not any("restore" in st for st in load_golden(p)["steps"])]
+    from conftest import golden_files
+    return golden_files()
 
 
 @pytest.mark.parametrize("path", _golden_paths(), ids=lambda p: os.path.basename(p)[:-8])
 def test_device_functions_replay_reference_golden(hostdev, path):
     """The reference-generated golden trajectories (tools/gen_golden.py ran the unmodified reference and recorded its
     uniform draws) through the host-compiled device code in parity mode: available mask before every step, whether the
-    option ran (the reference's None), reward, primitive ticks, done (treasure_game.py:95), the float32 observation and
-    the number of draws consumed, every step.  (The init_with_state trajectories stay with the -m gpu replay.)"""
-    from conftest import golden_level, load_golden
+    option ran (the reference's None), reward, primitive ticks, done (treasure_game.py:95), the float32 observation, the
+    full state snapshot (float64 angles, ordered bag, previously_triggered flags) and the number of draws consumed, every
+    step, incl. the init_with_state calls of the "restore" trajectories (impl:447-481, quirks and all)."""
+    from conftest import golden_level, load_golden, norm_snap
     rec = load_golden(path)
     lvt = golden_level(rec)
     cl = _compiled(lvt)
@@ -185,10 +229,18 @@ def test_device_functions_replay_reference_golden(hostdev, path):
         hostdev.hostdev_reset(h, None)                    # the reference constructor's draws
         hostdev.hostdev_reset(h, _ptr(obs))               # TreasureGame.reset()
         np.testing.assert_array_equal(obs[0], np.asarray(rec["init"]["obs"], dtype=np.float32))
+        assert _snapshot(hostdev, h, info) == norm_snap(rec["init"]["snap"])
         a = np.zeros(1, np.int32)
         for t, st in enumerate(rec["steps"]):
             hostdev.hostdev_mask(h, _ptr(mask))
             assert mask[0].tolist() == st["mask"], t
+            if "restore" in st:
+                states = np.asarray([st["restore"]], dtype=np.float64)
+                hostdev.hostdev_init_with_state(h, _ptr(states))
+                assert _snapshot(hostdev, h, info) == norm_snap(st["snap"]), t
+                hostdev.hostdev_flags(h, _ptr(err), _ptr(draws))
+                assert int(draws[0]) == st["draws"], t
+                continue
             a[0] = st["a"]
             hostdev.hostdev_step(h, _ptr(a), _ptr(obs), _ptr(rew), _ptr(done), _ptr(ran), _ptr(ticks))
             assert bool(ran[0]) == (st["r"] is not None), t
@@ -197,7 +249,38 @@ def test_device_functions_replay_reference_golden(hostdev, path):
                 assert int(ticks[0]) == st["ticks"], t
             assert bool(done[0] & 1) == st["done"], t
             np.testing.assert_array_equal(obs[0], np.asarray(st["obs"], dtype=np.float32), err_msg=str(t))
+            assert _snapshot(hostdev, h, info) == norm_snap(st["snap"]), t
             hostdev.hostdev_flags(h, _ptr(err), _ptr(draws))
             assert int(draws[0]) == st["draws"] and not err[0], t
+    finally:
+        hostdev.hostdev_destroy(h)
+
+
+def test_primitive_tick_matches_c_oracle(hostdev):
+    """tick() in its general form (impl:290-359, INTERACT included) as tg_primitive_step drives it: one raw action per
+    env per call, 768 envs x 900 calls, against the C oracle's prim_step; full state every 150 calls."""
+    lvt = po.default_level()
+    n, seed = 768, 909
+    cl = _compiled(lvt)
+    info = cl.info
+    blob = C.string_at(cl.handle, hostdev.hostdev_blob_size())
+    h = hostdev.hostdev_create(blob, None, 0, n, 0, seed, 400, 1, info.frame_w, info.frame_h)
+    cb = c_oracle.CBatch(c_oracle.CLevel(lvt), n, first_env_id=0, seed=seed, max_episode_steps=400, auto_reset=True)
+    try:
+        obs = np.zeros((n, info.obs_dim), np.float32)
+        rew = np.zeros(n, np.float32); done = np.zeros(n, np.uint8)
+        hostdev.hostdev_reset(h, _ptr(obs))
+        cb.reset()
+        rng = np.random.default_rng(12)
+        w = np.array([1.0, 2, 3, 4, 4, 1, 1, 0.2]); w /= w.sum()         # id 7 is not an action: falls through like NOP
+        for t in range(900):
+            a = rng.choice(8, size=n, p=w).astype(np.int32)
+            hostdev.hostdev_primitive_step(h, _ptr(a), _ptr(obs), _ptr(rew), _ptr(done))
+            o2, r2, d2 = cb.prim_step(a)
+            np.testing.assert_array_equal(rew, r2, err_msg=str(t))
+            np.testing.assert_array_equal(done, d2, err_msg=str(t))
+            np.testing.assert_array_equal(obs, o2.astype(np.float32), err_msg=str(t))
+            if t % 150 == 149:
+                _assert_state_equal(hostdev, h, cb, "tick %d" % t)
     finally:
         hostdev.hostdev_destroy(h)
