@@ -105,6 +105,15 @@ def _compiled(lvt):
     return CompiledLevel(product_level(lvt), with_sprites=False)
 
 
+def _blob(hostdev, cl):
+    """The level's LevelBlob bytes: tg_level begins with its LevelBlob (csrc/tg_capi.cu).  Checked, not assumed: the two
+    int16 behind the 32 x 32 tile table are the grid size."""
+    blob = C.string_at(cl.handle, hostdev.hostdev_blob_size())
+    cw, ch = np.frombuffer(blob, dtype=np.int16, count=2, offset=32 * 32)
+    assert (int(cw), int(ch)) == (cl.info.cw, cl.info.ch), "tg_level no longer starts with its LevelBlob"
+    return blob
+
+
 def _closure_table(cl, n_objs):
     """The level's closure table, entry by entry through the library's debug accessor."""
     from gym_treasure_game_b200 import _lib
@@ -135,8 +144,7 @@ def _levels():
 
 def _run(hostdev, lvt, n, steps, seed, max_steps, with_closure, first_env_id=0):
     cl = _compiled(lvt)
-    size = hostdev.hostdev_blob_size()
-    blob = C.string_at(cl.handle, size)            # tg_level begins with its LevelBlob (csrc/tg_capi.cu)
+    blob = _blob(hostdev, cl)
     info = cl.info
     tab = _closure_table(cl, info.n_objects) if with_closure else None
     h = hostdev.hostdev_create(blob, _ptr(tab) if tab is not None else None, 0 if tab is None else tab.size, n,
@@ -216,7 +224,7 @@ def test_device_functions_replay_reference_golden(hostdev, path):
     lvt = golden_level(rec)
     cl = _compiled(lvt)
     info = cl.info
-    blob = C.string_at(cl.handle, hostdev.hostdev_blob_size())
+    blob = _blob(hostdev, cl)
     h = hostdev.hostdev_create(blob, None, 0, 1, 0, 1, 0, 0, info.frame_w, info.frame_h)
     try:
         tape = np.asarray(rec["tape"], dtype=np.float64)
@@ -263,7 +271,7 @@ def test_primitive_tick_matches_c_oracle(hostdev):
     n, seed = 768, 909
     cl = _compiled(lvt)
     info = cl.info
-    blob = C.string_at(cl.handle, hostdev.hostdev_blob_size())
+    blob = _blob(hostdev, cl)
     h = hostdev.hostdev_create(blob, None, 0, n, 0, seed, 400, 1, info.frame_w, info.frame_h)
     cb = c_oracle.CBatch(c_oracle.CLevel(lvt), n, first_env_id=0, seed=seed, max_episode_steps=400, auto_reset=True)
     try:
