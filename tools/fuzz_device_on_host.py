@@ -2,7 +2,8 @@
 """Offline fuzz campaign for the kernels' device functions WITHOUT a GPU: random levels (tests/level_fuzz.py) through the
 host build of csrc/tg_device.cuh (tests/hostdev/hostdev.cpp) against the C oracle, bit-exact after every step -- the test
 tests/test_device_code_on_host.py::test_device_functions_match_c_oracle on many more levels, with drops and jumps weighted
-up.  usage: fuzz_device_on_host.py FIRST_SEED LAST_SEED [envs] [steps]      (one process per seed range; ~0.4 s per level)"""
+up.  usage: fuzz_device_on_host.py FIRST_SEED LAST_SEED [envs] [steps] [closure]     (one process per seed range; ~0.4 s per
+level; `closure`: INTERACT through the level's closure table, levels with triggers only, ~0.6 s per level)"""
 import os
 import sys
 import time
@@ -22,6 +23,7 @@ def main():
     lo, hi = int(sys.argv[1]), int(sys.argv[2])
     n = int(sys.argv[3]) if len(sys.argv) > 3 else 256
     steps = int(sys.argv[4]) if len(sys.argv) > 4 else 160
+    closure = len(sys.argv) > 5 and sys.argv[5] == "closure"
     L = C.CDLL(T._build())
     L.hostdev_blob_size.restype = C.c_size_t
     L.hostdev_create.restype = C.c_void_p
@@ -31,15 +33,16 @@ def main():
     L.hostdev_step.argtypes = [C.c_void_p] * 7
     L.hostdev_mask.argtypes = [C.c_void_p, C.c_void_p]
     L.hostdev_flags.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hostdev_state.argtypes = [C.c_void_p] * 10
     T.RARE_WEIGHT = np.array([1, 1, 2, 2, 1, 12, 12, 12, 12], dtype=np.float64)
     ok = bad = 0
     t0 = time.time()
     for s in range(lo, hi):
         lv = random_level(s)
-        if not usable(lv):
+        if not usable(lv) or (closure and not lv.triggers):
             continue
         try:
-            T._run(L, lv, n=n, steps=steps, seed=s * 7 + 1, max_steps=60 if s % 2 else 0, with_closure=False, first_env_id=s)
+            T._run(L, lv, n=n, steps=steps, seed=s * 7 + 1, max_steps=60 if s % 2 else 0, with_closure=closure, first_env_id=s)
             ok += 1
         except AssertionError as e:
             bad += 1
